@@ -1,0 +1,187 @@
+/*
+ * spectralkit_b200.h — C ABI of the B200-native (sm_100a) batched basis-evaluation library.
+ *
+ * The reference (tpapp/SpectralKit.jl v0.16.2) has no FFI or plugin interface: its boundary is
+ * the set of exported Julia generic functions (src/generic_api.jl:5-7) plus the constructors of
+ * bases, transformations and derivative requests.  This header is the C boundary a Julia
+ * `ccall` shim (spectralkit.jl_b200/julia/SpectralKitB200.jl), the Python `ctypes` mirror
+ * (spectralkit.jl_b200/api.py) or any C caller binds.  Every entry point cites the reference
+ * lines whose semantics it reproduces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - all floating point is IEEE binary64; all indices returned are 1-based like Julia's;
+ *   - every function returns an int status (SK_OK == 0); sk_last_error() gives a thread-local
+ *     message.  SK_ERR_ARGUMENT ↔ Julia ArgumentError, SK_ERR_DOMAIN ↔ DomainError,
+ *     SK_ERR_UNSUPPORTED ↔ `error("… not implemented yet")` / MethodError;
+ *   - the caller owns every buffer; the library keeps nothing but what is inside a plan;
+ *   - plans are immutable after creation and may be used concurrently from several threads,
+ *     each call on its own stream;
+ *   - there is NO CPU fallback: evaluation entry points fail with SK_ERR_NO_DEVICE /
+ *     SK_ERR_CUDA if no usable sm_100 device exists.  Only integer metadata and grids
+ *     (initialisation-time, tiny) are computed on the host.
+ *
+ * Memory layouts (identical to the Julia object layouts, so a shim passes pointers through)
+ *   points   x   : univariate [n]; Smolyak [n][d]   (Vector{NTuple{d,Float64}} / d×n Matrix)
+ *   coeffs   θ   : [K][nvec], nvec fastest          (Vector{Float64} / Vector{SVector{nvec}})
+ *   lincomb  out : [n][E]  with E = D+1 (𝑑Expansion), ncomp (∂Expansion), or nvec (SVector)
+ *   basis_at out : column-major n×K matrix of E-double elements: out[(k*n + i)*E + q]
+ *                  (= Matrix{Float64|𝑑Expansion|∂Expansion}, src/generic_api.jl:217-227)
+ */
+#ifndef SPECTRALKIT_B200_H
+#define SPECTRALKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_MAX_DIM 16        /* Smolyak dimension d */
+#define SK_MAX_BLOCKS 8      /* block cap M */
+#define SK_MAX_ORDER 5       /* univariate derivative order D (test/test_chebyshev.jl:93 uses 5) */
+#define SK_MAX_COMP 64       /* components of a ∂ specification */
+
+enum sk_status {
+    SK_OK = 0,
+    SK_ERR_ARGUMENT = -1,
+    SK_ERR_DOMAIN = -2,
+    SK_ERR_UNSUPPORTED = -3,
+    SK_ERR_CUDA = -4,
+    SK_ERR_NO_DEVICE = -5,
+    SK_ERR_NCCL = -6
+};
+
+enum sk_basis_kind { SK_BASIS_CHEBYSHEV = 0, SK_BASIS_SMOLYAK = 1 };
+/* src/generic_api.jl:174-192 */
+enum sk_grid_kind { SK_GRID_INTERIOR = 0, SK_GRID_ENDPOINT = 1, SK_GRID_INTERIOR2 = 2 };
+/* src/transformations.jl:149,206,280 */
+enum sk_transform_kind { SK_TR_NONE = 0, SK_TR_BOUNDED_LINEAR = 1, SK_TR_SEMI_INF_RATIONAL = 2, SK_TR_INF_RATIONAL = 3 };
+
+/* Chebyshev(grid_kind, N) (src/chebyshev.jl:12-32) or
+ * smolyak_basis(Chebyshev, grid_kind, SmolyakParameters(B, M), d) (src/smolyak_api.jl:63-75). */
+typedef struct sk_basis_desc {
+    int32_t kind;       /* sk_basis_kind */
+    int32_t grid_kind;  /* sk_grid_kind */
+    int32_t N;          /* Chebyshev: number of basis functions, >= 1 */
+    int32_t d;          /* Smolyak: dimension, 1..SK_MAX_DIM */
+    int32_t B;          /* Smolyak: sum of block indices <= B */
+    int32_t M;          /* Smolyak: each block index <= M (M > B is clamped, smolyak_traversal.jl:15-16) */
+} sk_basis_desc;
+
+/* The reference's stored fields: BoundedLinear (m, s) (transformations.jl:150-153);
+ * SemiInfRational / InfRational (A, L) (:207-210, :281-284). */
+typedef struct sk_transform {
+    int32_t kind;       /* sk_transform_kind */
+    int32_t reserved;
+    double p0;          /* m or A */
+    double p1;          /* s or L */
+} sk_transform;
+
+/* Derivative request.
+ *   Chebyshev: `order` = D of 𝑑^D (src/derivatives.jl:66-107); ncomp/orders ignored.
+ *   Smolyak:   ncomp == 0 → a plain point (no ∂); otherwise the canonical expansion of a
+ *              ∂ specification (src/derivatives.jl:284-300): orders[c*d + j] = derivative order
+ *              of component c along coordinate j.  sk_partials_canonical builds it. */
+typedef struct sk_deriv_spec {
+    int32_t order;
+    int32_t ncomp;
+    const int32_t *orders;
+    int32_t allow_rational_d2;  /* EXTENSION: 2nd derivatives through the rational maps (the
+                                   reference throws, transformations.jl:266,332); 0 = reference behaviour */
+} sk_deriv_spec;
+
+typedef struct sk_plan sk_plan;  /* opaque */
+
+typedef struct sk_plan_info {
+    int32_t kind, grid_kind, d, B, M, device;
+    int64_t K;              /* dimension(basis) */
+    int64_t H;              /* parent dimension (Smolyak) or N */
+    int32_t E;              /* doubles per output element for nvec == 1 */
+    int32_t fast_path;      /* 1 if the nested (run-structured) kernel serves linear_combination */
+    int64_t n_runs;         /* level-1 runs of the traversal (K_2) */
+    double flops_per_point_fast;    /* closed-form FP64 flop count of the fast kernel, per point */
+    double flops_per_point_direct;  /* F_direct of SURVEY.md §8(d): what the reference executes */
+    double bytes_per_point;         /* algorithmic HBM bytes per point: 8*d + 8*E */
+} sk_plan_info;
+
+/* flags for the evaluation entry points */
+#define SK_MEM_HOST 0u          /* x, theta, out are host pointers; copies happen inside the call */
+#define SK_MEM_DEVICE 1u        /* x, theta, out are device pointers on the plan's device */
+#define SK_MODE_FAST 0u         /* FMA-contracted, nested evaluation; within the stated tolerance */
+#define SK_MODE_EXACT 2u        /* reference operation order, no contraction: bit-identical to the
+                                   reference restatement (sequential sum, mul-then-add) */
+
+/* ---------------------------------------------------------------- library */
+const char *sk_version(void);
+const char *sk_last_error(void);           /* thread-local */
+int sk_device_count(int *count);           /* SK_ERR_NO_DEVICE if no CUDA device */
+
+/* ---------------------------------------------------------------- constructors, metadata (host) */
+/* BoundedLinear(a,b) / SemiInfRational(A,L) / InfRational(A,L) with the reference's DomainError
+ * checks (transformations.jl:154-161, 211-215, 285-289). */
+int sk_transform_make(int kind, double a, double b, sk_transform *out);
+/* nesting_total_length / nesting_block_length (smolyak_traversal.jl:69-84,112-116,146-148) */
+int sk_nesting_total_length(int grid_kind, int b, int64_t *out);
+int sk_nesting_block_length(int grid_kind, int b, int64_t *out);
+/* collect(SmolyakGridShuffle(grid_kind, len)) (smolyak_traversal.jl:86-168); out[len] */
+int sk_grid_shuffle(int grid_kind, int64_t len, int64_t *out);
+/* dimension(basis) (chebyshev.jl:34, smolyak_api.jl:82, smolyak_traversal.jl:238-256) */
+int sk_dimension(const sk_basis_desc *basis, int64_t *K);
+/* highest_visited_index / parent Chebyshev dimension (smolyak_traversal.jl:307,317) */
+int sk_parent_dimension(const sk_basis_desc *basis, int64_t *H);
+/* collect(SmolyakIndices) (smolyak_traversal.jl:294-334): out[K][d], 1-based, traversal order */
+int sk_smolyak_indices(const sk_basis_desc *basis, int32_t *out);
+/* collect(grid(basis ∘ transformations)) (chebyshev.jl:88-127, smolyak_api.jl:121-135,
+ * generic_api.jl:296-300).  tr == NULL → untransformed.  out[N] or out[K][d].
+ * sinpi/cospi are correctly rounded at the rounded Float64 argument. */
+int sk_grid(const sk_basis_desc *basis, const sk_transform *tr, double *out);
+/* ∂ algebra: minimal representation + canonical expansion + per-coordinate degrees
+ * (derivatives.jl:266-316).  partials[np][d] (trailing zeros allowed); out_orders[cap][d]. */
+int sk_partials_canonical(int d, int np, const int32_t *partials, int32_t *out_orders, int cap,
+                          int32_t *ncomp, int32_t *degrees);
+
+/* ---------------------------------------------------------------- plans */
+/* tr: NULL (untransformed basis) or 1 (Chebyshev) / d (Smolyak) transformations: basis ∘ t
+ * (generic_api.jl:263-274).  spec: NULL = values only. */
+int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_deriv_spec *spec,
+                   int device, sk_plan **out);
+int sk_plan_destroy(sk_plan *plan);
+int sk_plan_get_info(const sk_plan *plan, sk_plan_info *info);
+
+/* ---------------------------------------------------------------- the hot path (GPU only) */
+/* linear_combination(basis, θ, x) for n points (generic_api.jl:114-138).  nvec > 1 is the
+ * SVector-coefficient case (derivatives.jl:15,19; values only).  `theta_len` is checked against
+ * dimension(basis): SK_ERR_ARGUMENT "not enough/too many coefficients" (generic_api.jl:99-102). */
+int sk_linear_combination(const sk_plan *plan, const double *theta, int64_t theta_len, int nvec,
+                          const double *x, int64_t n, double *out, uint32_t flags, void *stream);
+/* collocation_matrix(basis, x) == basis_at at n points (generic_api.jl:217-227); always in the
+ * reference's operation order (bit-identical basis values).  ld = leading dimension in elements
+ * (>= n). */
+int sk_basis_at(const sk_plan *plan, const double *x, int64_t n, double *out, int64_t ld,
+                uint32_t flags, void *stream);
+/* transform_to / transform_from over n points of d coordinates (transformations.jl:112-139,
+ * 178-195, 244-267, 309-333).  order = D of the seeded jets for transform_to:
+ * out[n][d][D+1]; transform_from: out[n][d]. */
+int sk_transform_to(const sk_transform *tr, int d, int order, int allow_rational_d2, const double *y,
+                    int64_t n, double *out, uint32_t flags, int device, void *stream);
+int sk_transform_from(const sk_transform *tr, int d, const double *x, int64_t n, double *out,
+                      uint32_t flags, int device, void *stream);
+
+/* ---------------------------------------------------------------- multi-GPU (one process, G devices) */
+/* Points are independent: contiguous slices of ceil(n/G) points per device, plans replicated,
+ * θ copied to each device, no reduction, outputs land in the caller's host buffer.
+ * plans[g] must live on distinct devices.  Host pointers only. */
+int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double *theta, int64_t theta_len,
+                                  int nvec, const double *x, int64_t n, double *out, uint32_t flags);
+
+/* ---------------------------------------------------------------- measurement helpers */
+/* Measures the FP64 pipe on `device`: which = 0 DFMA (CUDA-core), 1 DMMA (mma.sync m8n8k4 f64).
+ * Runs for about `seconds`; returns TFLOP/s of the best (burst) and of the whole loop (sustained). */
+int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained);
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t sk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRALKIT_B200_H */

@@ -1,0 +1,72 @@
+// Internal declarations shared by the host plan builder (sk_host.cpp), the kernels
+// (sk_kernels.cu) and the C-ABI layer (sk_api.cu).  Not part of the public boundary.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "spectralkit_b200.h"
+
+namespace skh {
+
+// ---- errors (thread-local message, status code returned through the C ABI)
+void set_error(const std::string &msg);
+const char *last_error();
+#define SK_FAIL(code, msg) do { ::skh::set_error(msg); return (code); } while (0)
+
+// ---- block structure of the nested univariate families (smolyak_traversal.jl:69-84,112-116,146-148)
+int64_t total_length(int grid_kind, int b);   // ℓ(b); -1 on bad kind
+int64_t block_length(int grid_kind, int b);
+// permutation of 1..len putting nested grids first (smolyak_traversal.jl:86-168); false if len is
+// not a cumulative block length of that family
+bool grid_shuffle(int grid_kind, int64_t len, std::vector<int64_t> &out);
+// correctly rounded Chebyshev grid point i (1-based) of an N-point grid (chebyshev.jl:88-108)
+double gridpoint(int grid_kind, int64_t N, int64_t i);
+
+// ---- Smolyak index set in the reference's traversal order (column-major, i_1 fastest)
+struct SmolyakSet {
+    int grid_kind = 0, d = 0, B = 0, M = 0;
+    int64_t H = 0;                 // ℓ(M)
+    int64_t K = 0;                 // number of index tuples
+    std::vector<int64_t> ell;      // ℓ(0..M)
+    std::vector<uint16_t> idx;     // [K][d], 1-based
+    // run structure: one run per distinct tail (i_2..i_d)
+    //   run_len[r]   = ℓ(min(slack, M)) terms of θ, contiguous
+    //   run_carry[r] = number of levels 2,3,… that wrap to index 1 when advancing to run r+1
+    std::vector<uint32_t> run_len;
+    std::vector<uint8_t> run_carry;
+    std::vector<int64_t> Kj;       // K_j, j = 1..d (number of distinct suffixes (i_j..i_d)), Kj[0] = K
+};
+// count only (no enumeration): the number of tuples
+int64_t smolyak_count(int grid_kind, int d, int B, int M);
+bool smolyak_enumerate(int grid_kind, int d, int B, int M, SmolyakSet &out, bool want_idx = true);
+
+// ---- ∂ specification algebra (derivatives.jl:228-316)
+// partials: np rows of d ints (trailing zeros allowed).  Produces the canonical component table
+// (row-major [ncomp][d]) and per-coordinate degrees.  Returns false on invalid input.
+bool partials_canonical(int d, int np, const int32_t *partials, std::vector<int32_t> &orders,
+                        std::vector<int32_t> &degrees);
+
+}  // namespace skh
+
+// ---- the plan object behind the opaque handle
+struct sk_plan {
+    sk_basis_desc basis{};       // normalised (M clamped to B)
+    int device = 0;
+    bool has_tr = false;
+    sk_transform tr[SK_MAX_DIM]{};
+    int order = 0;               // univariate D
+    int ncomp = 0;               // Smolyak: 0 = plain point
+    int32_t orders[SK_MAX_COMP][SK_MAX_DIM]{};
+    int32_t deg[SK_MAX_DIM]{};   // per-coordinate jet order
+    int allow_d2 = 0;
+    int E = 1;                   // doubles per output element (nvec == 1)
+    int64_t K = 0, H = 0;
+    int fast_mode = -1;          // Smolyak nested kernel: -1 unavailable, 0 values, 1 value+gradient
+    skh::SmolyakSet set;
+    // device tables (Smolyak)
+    uint16_t *d_idx = nullptr;   // [K][d]
+    uint32_t *d_runs = nullptr;  // [n_runs] run_len | carry << 24
+    int64_t n_runs = 0;
+    double flops_fast = 0, flops_direct = 0;
+};

@@ -1,0 +1,562 @@
+// sm_100a kernels, part 1: univariate Chebyshev paths, the reference-order (direct) Smolyak
+// paths, batched coordinate transformations and the FP64 pipe microbenchmarks.
+//
+// Compiled with -fmad=false (see sk_device.cuh): "exact" kernels reproduce the reference's
+// unfused operation order bit for bit; "fast" kernels use explicit fma().
+//
+// Kernel map:
+//   K1  uni_lincomb_kernel        fused transform + recurrence + dot (generic_api.jl:114-128,
+//                                 chebyshev.jl:60-70, transformations.jl:183-333)
+//   K3  uni_basis_kernel /        collocation_matrix rows (generic_api.jl:217-227), streamed out
+//       smolyak_direct_kernel<BASIS>  with the bulk-copy engine (cp.async.bulk smem→global)
+//   K2' smolyak_direct_kernel     direct-form Smolyak product + sequential dot in the reference's
+//                                 order (smolyak_traversal.jl:373-379, derivatives.jl:491,502-511)
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+
+#include "sk_device.cuh"
+#include "sk_launch.h"
+
+namespace skk {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+using skd::Jet;
+
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && cached[dev]) return cached[dev];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 64) cached[dev] = n;
+    return n;
+}
+
+// -------------------------------------------------------------------------------------------
+// bulk-copy (TMA engine, non-tensor form) helpers: shared::cta → global, bulk-group completion
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// -------------------------------------------------------------------------------------------
+// K1: univariate linear combination, one point per thread, θ staged in shared memory
+// -------------------------------------------------------------------------------------------
+template <int DP1, bool EXACT>
+__global__ void __launch_bounds__(256) uni_lincomb_kernel(int N, sk_transform tr, const double *__restrict__ theta,
+                                                          int theta_in_smem, const double *__restrict__ x, int64_t n,
+                                                          double *__restrict__ out) {
+    extern __shared__ double s_theta[];
+    const double *th = theta;
+    if (theta_in_smem) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_theta[i] = theta[i];
+        __syncthreads();
+        th = s_theta;
+    }
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        double xj[DP1];
+        skd::to_pm1_jet<DP1>(tr, x[p], xj);
+        double s[DP1];
+        if (EXACT) {
+            // generic_api.jl:114-128: s = θ₁·b₁; s = s + θ_k·b_k, jets in the reference's order
+            Jet<DP1> X, fp = skd::jet_one<DP1>(), fpp;
+#pragma unroll
+            for (int r = 0; r < DP1; r++) { X.c[r] = xj[r]; fpp.c[r] = xj[r]; }
+            double th0 = th[0];
+#pragma unroll
+            for (int r = 0; r < DP1; r++) s[r] = th0 * fp.c[r];
+            for (int k = 1; k < N; k++) {
+                Jet<DP1> f = skd::cheb_step_exact<DP1>(X, fp, fpp);
+                fpp = fp; fp = f;
+                double tk = th[k];
+#pragma unroll
+                for (int r = 0; r < DP1; r++) s[r] = s[r] + tk * f.c[r];
+            }
+        } else {
+            // same recurrence with explicit fma contraction (DP1 <= 3)
+            double t0 = 2.0 * xj[0];
+            double t1 = DP1 > 1 ? 2.0 * xj[DP1 > 1 ? 1 : 0] : 0.0;
+            double tt1 = 2.0 * t1;                                     // binom(2,1)·t1
+            double t2 = DP1 > 2 ? 2.0 * xj[DP1 > 2 ? 2 : 0] : 0.0;
+            double fp[DP1], fpp[DP1];
+#pragma unroll
+            for (int r = 0; r < DP1; r++) { fp[r] = r == 0 ? 1.0 : 0.0; fpp[r] = xj[r]; }
+            double th0 = th[0];
+#pragma unroll
+            for (int r = 0; r < DP1; r++) s[r] = r == 0 ? th0 : 0.0;
+#pragma unroll 4
+            for (int k = 1; k < N; k++) {
+                double f[DP1];
+                f[0] = fma(t0, fp[0], -fpp[0]);
+                if (DP1 > 1) f[DP1 > 1 ? 1 : 0] = fma(t0, fp[DP1 > 1 ? 1 : 0], fma(t1, fp[0], -fpp[DP1 > 1 ? 1 : 0]));
+                if (DP1 > 2)
+                    f[DP1 > 2 ? 2 : 0] = fma(t0, fp[DP1 > 2 ? 2 : 0],
+                                             fma(tt1, fp[DP1 > 1 ? 1 : 0], fma(t2, fp[0], -fpp[DP1 > 2 ? 2 : 0])));
+                double tk = th[k];
+#pragma unroll
+                for (int r = 0; r < DP1; r++) { s[r] = fma(tk, f[r], s[r]); fpp[r] = fp[r]; fp[r] = f[r]; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < DP1; r++) out[p * DP1 + r] = s[r];
+    }
+}
+
+// SVector coefficients (nvec > 1), values only: θ is [N][nvec]; VC vectors per pass
+template <bool EXACT, int VC>
+__global__ void __launch_bounds__(256) uni_lincomb_nvec_kernel(int N, sk_transform tr, const double *__restrict__ theta,
+                                                               int nvec, const double *__restrict__ x, int64_t n,
+                                                               double *__restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        double x0 = skd::to_pm1(tr, x[p]);
+        double t0 = 2.0 * x0;
+        for (int v0 = 0; v0 < nvec; v0 += VC) {
+            double s[VC];
+            double fp = 1.0, fpp = x0;
+#pragma unroll
+            for (int v = 0; v < VC; v++) s[v] = (v0 + v < nvec) ? theta[v0 + v] * 1.0 : 0.0;
+            for (int k = 1; k < N; k++) {
+                double f = EXACT ? (t0 * fp - fpp) : fma(t0, fp, -fpp);
+                fpp = fp; fp = f;
+                const double *tk = theta + (size_t)k * nvec + v0;
+#pragma unroll
+                for (int v = 0; v < VC; v++)
+                    if (v0 + v < nvec) s[v] = EXACT ? (s[v] + tk[v] * f) : fma(tk[v], f, s[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < VC; v++)
+                if (v0 + v < nvec) out[p * nvec + v0 + v] = s[v];
+        }
+    }
+}
+
+template <int DP1>
+static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const double *theta, const double *x, int64_t n,
+                              double *out, cudaStream_t stream) {
+    int threads = 256;
+    int64_t want = (n + threads - 1) / threads;
+    int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 16);
+    size_t smem = (size_t)N * sizeof(double);
+    int in_smem = smem <= 48 * 1024;
+    if (!in_smem) smem = 0;
+    if (exact) uni_lincomb_kernel<DP1, true><<<grid, threads, smem, stream>>>(N, tr, theta, in_smem, x, n, out);
+    else uni_lincomb_kernel<(DP1 <= 3 ? DP1 : 1), false><<<grid, threads, smem, stream>>>(N, tr, theta, in_smem, x, n, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t uni_lincomb(int N, const sk_transform &tr, int order, bool exact, const double *theta, int nvec,
+                        const double *x, int64_t n, double *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (nvec > 1) {
+        int threads = 256;
+        int grid = (int)std::min<int64_t>((n + threads - 1) / threads, (int64_t)sm_count() * 16);
+        if (exact) uni_lincomb_nvec_kernel<true, 8><<<grid, threads, 0, stream>>>(N, tr, theta, nvec, x, n, out);
+        else uni_lincomb_nvec_kernel<false, 8><<<grid, threads, 0, stream>>>(N, tr, theta, nvec, x, n, out);
+        count_launch();
+        return cudaGetLastError();
+    }
+    if (order > 2) exact = true;   // the contracted recurrence is written out for D <= 2 only
+    switch (order) {
+    case 0: return launch_uni<1>(exact, N, tr, theta, x, n, out, stream);
+    case 1: return launch_uni<2>(exact, N, tr, theta, x, n, out, stream);
+    case 2: return launch_uni<3>(exact, N, tr, theta, x, n, out, stream);
+    case 3: return launch_uni<4>(exact, N, tr, theta, x, n, out, stream);
+    case 4: return launch_uni<5>(exact, N, tr, theta, x, n, out, stream);
+    case 5: return launch_uni<6>(exact, N, tr, theta, x, n, out, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// -------------------------------------------------------------------------------------------
+// K3 (univariate): collocation matrix.  One point per thread, basis functions produced in order by
+// the exact recurrence; each block stages a tile of P points × E doubles per basis function in
+// shared memory (triple buffered) and one elected thread streams it out with the bulk-copy engine.
+// Falls back to plain coalesced stores when the tile is partial or the destination is not 16-byte
+// aligned.  out[(j*ld + i)*E + r].
+// -------------------------------------------------------------------------------------------
+template <int DP1>
+__global__ void __launch_bounds__(128) uni_basis_kernel(int N, sk_transform tr, const double *__restrict__ x, int64_t n,
+                                                        double *__restrict__ out, int64_t ld) {
+    constexpr int P = 128;
+    __shared__ __align__(128) double stage[3][P * DP1];
+    const int tid = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * P;
+    const int64_t p = p0 + tid;
+    const bool full = p0 + P <= n;
+    const bool live = p < n;
+    Jet<DP1> X, fp = skd::jet_one<DP1>(), fpp, f = fp;
+    {
+        double xj[DP1];
+        skd::to_pm1_jet<DP1>(tr, live ? x[p] : 0.0, xj);
+#pragma unroll
+        for (int r = 0; r < DP1; r++) { X.c[r] = xj[r]; fpp.c[r] = xj[r]; }
+    }
+    for (int j = 0; j < N; j++) {
+        if (j > 0) { f = skd::cheb_step_exact<DP1>(X, fp, fpp); fpp = fp; fp = f; }
+        double *g = out + ((size_t)j * ld + p0) * DP1;
+        const bool bulk = full && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);     // block-uniform
+        if (bulk) {
+            double *st = stage[j % 3];
+#pragma unroll
+            for (int r = 0; r < DP1; r++) st[tid * DP1 + r] = f.c[r];
+            bulk_store_fence();
+            __syncthreads();
+            if (tid == 0) { bulk_store(g, st, P * DP1 * 8); bulk_store_wait_read_1(); }
+        } else if (live) {
+#pragma unroll
+            for (int r = 0; r < DP1; r++) g[tid * DP1 + r] = f.c[r];
+        }
+    }
+    if (tid == 0) bulk_store_wait_all();
+}
+
+cudaError_t uni_basis_at(int N, const sk_transform &tr, int order, const double *x, int64_t n, double *out, int64_t ld,
+                         cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    int grid = (int)((n + 127) / 128);
+    switch (order) {
+    case 0: uni_basis_kernel<1><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    case 1: uni_basis_kernel<2><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    case 2: uni_basis_kernel<3><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    case 3: uni_basis_kernel<4><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    case 4: uni_basis_kernel<5><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    case 5: uni_basis_kernel<6><<<grid, 128, 0, stream>>>(N, tr, x, n, out, ld); break;
+    default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
+// K2' / K3 (Smolyak): direct form in the reference's operation order.
+//   * d univariate tables of H jets per point (smolyak_api.jl:89-93) live in shared memory,
+//     laid out [dim][index][order][point] so a warp's reads are conflict free;
+//   * the index table (K×d uint16, traversal order, built once by the plan) replaces the
+//     per-point `__inc` state machine (smolyak_traversal.jl:211-231); it is warp-uniform;
+//   * each component is the left-to-right product over dimensions (derivatives.jl:502-511), and
+//     the linear combination is the sequential s = s + θ_k·b_k (generic_api.jl:114-128).
+// -------------------------------------------------------------------------------------------
+struct DirectParams {
+    int d, H, ncomp, E;          // ncomp == 0: plain point (E = 1)
+    int64_t K, n, ld;
+    const uint16_t *idx;
+    const double *theta;
+    int nvec;
+    const double *x;
+    double *out;
+    int64_t k_chunk;             // BASIS: terms per blockIdx.y
+    sk_transform tr[SK_MAX_DIM];
+    int8_t orders[SK_MAX_COMP][SK_MAX_DIM];
+};
+
+template <int EMAX>
+__device__ __forceinline__ void build_tables(const DirectParams &q, const double *xp, bool live, double *tab, int P, int tid) {
+    for (int j = 0; j < q.d; j++) {
+        double xj[EMAX];
+        skd::to_pm1_jet<EMAX>(q.tr[j], live ? xp[j] : 0.0, xj);
+        Jet<EMAX> X, fp = skd::jet_one<EMAX>(), fpp, f = fp;
+#pragma unroll
+        for (int r = 0; r < EMAX; r++) { X.c[r] = xj[r]; fpp.c[r] = xj[r]; }
+        for (int i = 0; i < q.H; i++) {
+            if (i > 0) { f = skd::cheb_step_exact<EMAX>(X, fp, fpp); fpp = fp; fp = f; }
+#pragma unroll
+            for (int r = 0; r < EMAX; r++) tab[(((size_t)j * q.H + i) * EMAX + r) * P + tid] = f.c[r];
+        }
+    }
+}
+
+// product over dimensions of component c at term ik (left to right)
+template <int EMAX>
+__device__ __forceinline__ double term_product(const DirectParams &q, const uint16_t *ik, int c, const double *tab, int P, int tid) {
+    int o = q.ncomp ? q.orders[c][0] : 0;
+    double b = tab[(((size_t)0 * q.H + (ik[0] - 1)) * EMAX + o) * P + tid];
+    for (int j = 1; j < q.d; j++) {
+        o = q.ncomp ? q.orders[c][j] : 0;
+        b = b * tab[(((size_t)j * q.H + (ik[j] - 1)) * EMAX + o) * P + tid];
+    }
+    return b;
+}
+
+template <int EMAX, int NCMAX>
+__global__ void smolyak_direct_lincomb_kernel(const __grid_constant__ DirectParams q) {
+    extern __shared__ double tab[];
+    const int P = blockDim.x, tid = threadIdx.x;
+    const int nc = q.ncomp ? q.ncomp : 1;
+    for (int64_t p0 = (int64_t)blockIdx.x * P; p0 < q.n; p0 += (int64_t)gridDim.x * P) {
+        const int64_t p = p0 + tid;
+        const bool live = p < q.n;
+        __syncthreads();
+        build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid);
+        // (each thread only reads its own column: no barrier needed after the build)
+        if (q.nvec == 1) {
+            double s[NCMAX];
+            for (int64_t k = 0; k < q.K; k++) {
+                const uint16_t *ik = q.idx + (size_t)k * q.d;
+                double th = q.theta[k];
+#pragma unroll
+                for (int c = 0; c < NCMAX; c++)
+                    if (c < nc) {
+                        double b = term_product<EMAX>(q, ik, c, tab, P, tid);
+                        s[c] = k == 0 ? th * b : s[c] + th * b;
+                    }
+            }
+            if (live)
+#pragma unroll
+                for (int c = 0; c < NCMAX; c++)
+                    if (c < nc) q.out[(size_t)p * nc + c] = s[c];
+        } else {
+            // SVector coefficients: plain points only (checked by the API layer); 8 vectors per pass
+            for (int v0 = 0; v0 < q.nvec; v0 += 8) {
+                double s[8];
+                for (int64_t k = 0; k < q.K; k++) {
+                    const uint16_t *ik = q.idx + (size_t)k * q.d;
+                    double b = term_product<EMAX>(q, ik, 0, tab, P, tid);
+                    const double *tk = q.theta + (size_t)k * q.nvec + v0;
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        if (v0 + v < q.nvec) s[v] = k == 0 ? tk[v] * b : s[v] + tk[v] * b;
+                }
+                if (live)
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        if (v0 + v < q.nvec) q.out[(size_t)p * q.nvec + v0 + v] = s[v];
+            }
+        }
+    }
+}
+
+// basis_at / collocation: blockIdx.x = tile of P points, blockIdx.y = chunk of terms.
+// Staging is [3][P*E] doubles after the tables.
+template <int EMAX>
+__global__ void smolyak_direct_basis_kernel(const __grid_constant__ DirectParams q) {
+    extern __shared__ double smem[];
+    const int P = blockDim.x, tid = threadIdx.x;
+    const int E = q.E;
+    double *tab = smem;
+    double *stage = smem + (size_t)q.d * q.H * EMAX * P;
+    const int64_t p0 = (int64_t)blockIdx.x * P, p = p0 + tid;
+    const bool live = p < q.n, full = p0 + P <= q.n;
+    build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid);
+    const int64_t k0 = (int64_t)blockIdx.y * q.k_chunk, k1 = min(q.K, k0 + q.k_chunk);
+    int buf = 0;
+    for (int64_t k = k0; k < k1; k++) {
+        const uint16_t *ik = q.idx + (size_t)k * q.d;
+        double *g = q.out + ((size_t)k * q.ld + p0) * E;
+        const bool bulk = full && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (((size_t)P * E * 8) % 16 == 0);
+        double *st = stage + (size_t)buf * P * E;
+        for (int c = 0; c < E; c++) {
+            double b = term_product<EMAX>(q, ik, c, tab, P, tid);
+            if (bulk) st[tid * E + c] = b;
+            else if (live) g[(size_t)tid * E + c] = b;
+        }
+        if (bulk) {
+            bulk_store_fence();
+            __syncthreads();
+            if (tid == 0) { bulk_store(g, st, (uint32_t)(P * E * 8)); bulk_store_wait_read_1(); }
+            buf = buf == 2 ? 0 : buf + 1;
+        }
+    }
+    if (tid == 0) bulk_store_wait_all();
+}
+
+static void fill_direct_params(const sk_plan &plan, DirectParams &q) {
+    q.d = plan.basis.d; q.H = (int)plan.H; q.ncomp = plan.ncomp; q.E = plan.ncomp ? plan.ncomp : 1;
+    q.K = plan.K; q.idx = plan.d_idx;
+    for (int j = 0; j < q.d; j++) {
+        if (plan.has_tr) q.tr[j] = plan.tr[j];
+        else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
+    }
+    for (int c = 0; c < plan.ncomp; c++) for (int j = 0; j < q.d; j++) q.orders[c][j] = (int8_t)plan.orders[c][j];
+}
+static int plan_emax(const sk_plan &plan) {
+    int e = 1;
+    for (int j = 0; j < plan.basis.d; j++) e = std::max(e, plan.deg[j] + 1);
+    return e <= 3 ? e : 6;
+}
+// points per block such that the tables (+ staging) fit in shared memory
+static int pick_points_per_block(size_t bytes_per_point, size_t limit) {
+    for (int P = 128; P >= 32; P >>= 1) if (bytes_per_point * P <= limit) return P;
+    return 0;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
+                                   double *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    DirectParams q{};
+    fill_direct_params(plan, q);
+    q.theta = theta; q.nvec = nvec; q.x = x; q.out = out; q.n = n; q.ld = n; q.k_chunk = q.K;
+    const int emax = plan_emax(plan);
+    size_t per_point = (size_t)q.d * q.H * emax * sizeof(double);
+    int P = pick_points_per_block(per_point, 200 * 1024);
+    if (!P) return cudaErrorInvalidConfiguration;
+    size_t smem = per_point * P;
+    int grid = (int)std::min<int64_t>((n + P - 1) / P, (int64_t)sm_count() * 8);
+    cudaError_t e = cudaSuccess;
+#define SK_LAUNCH_DL(EM, NC)                                                             \
+    do {                                                                                 \
+        e = set_smem(smolyak_direct_lincomb_kernel<EM, NC>, smem);                       \
+        if (e == cudaSuccess) smolyak_direct_lincomb_kernel<EM, NC><<<grid, P, smem, stream>>>(q); \
+    } while (0)
+    const int nc = q.ncomp ? q.ncomp : 1;
+    if (emax == 1) { if (nc <= 1) SK_LAUNCH_DL(1, 1); else if (nc <= 8) SK_LAUNCH_DL(1, 8); else SK_LAUNCH_DL(1, 64); }
+    else if (emax == 2) { if (nc <= 8) SK_LAUNCH_DL(2, 8); else if (nc <= 24) SK_LAUNCH_DL(2, 24); else SK_LAUNCH_DL(2, 64); }
+    else if (emax == 3) { if (nc <= 8) SK_LAUNCH_DL(3, 8); else if (nc <= 24) SK_LAUNCH_DL(3, 24); else SK_LAUNCH_DL(3, 64); }
+    else { if (nc <= 8) SK_LAUNCH_DL(6, 8); else SK_LAUNCH_DL(6, 64); }
+#undef SK_LAUNCH_DL
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld,
+                                    cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    DirectParams q{};
+    fill_direct_params(plan, q);
+    q.theta = nullptr; q.nvec = 1; q.x = x; q.out = out; q.n = n; q.ld = ld;
+    const int emax = plan_emax(plan);
+    size_t per_point = (size_t)q.d * q.H * emax * sizeof(double) + 3 * (size_t)q.E * sizeof(double);
+    int P = pick_points_per_block(per_point, 200 * 1024);
+    if (!P) return cudaErrorInvalidConfiguration;
+    size_t smem = per_point * P;
+    int64_t tiles = (n + P - 1) / P;
+    // enough blocks to fill the machine: split the K terms when there are few point tiles
+    int64_t want_chunks = std::max<int64_t>(1, ((int64_t)sm_count() * 2 + tiles - 1) / tiles);
+    int64_t chunks = std::min<int64_t>(want_chunks, std::max<int64_t>(1, q.K / 64));
+    chunks = std::min<int64_t>(chunks, 65535);
+    q.k_chunk = (q.K + chunks - 1) / chunks;
+    dim3 grid((unsigned)tiles, (unsigned)((q.K + q.k_chunk - 1) / q.k_chunk));
+    cudaError_t e;
+#define SK_LAUNCH_DB(EM)                                                   \
+    do {                                                                   \
+        e = set_smem(smolyak_direct_basis_kernel<EM>, smem);               \
+        if (e == cudaSuccess) smolyak_direct_basis_kernel<EM><<<grid, P, smem, stream>>>(q); \
+    } while (0)
+    if (emax == 1) SK_LAUNCH_DB(1); else if (emax == 2) SK_LAUNCH_DB(2); else if (emax == 3) SK_LAUNCH_DB(3); else SK_LAUNCH_DB(6);
+#undef SK_LAUNCH_DB
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
+// batched coordinate transformations (transformations.jl:112-139)
+// -------------------------------------------------------------------------------------------
+struct TrParams { int d; sk_transform tr[SK_MAX_DIM]; };
+
+template <int DP1>
+__global__ void transform_to_kernel(const __grid_constant__ TrParams q, const double *__restrict__ y, int64_t total,
+                                    double *__restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(e % q.d);
+        double xj[DP1];
+        skd::to_pm1_jet<DP1>(q.tr[j], y[e], xj);
+#pragma unroll
+        for (int r = 0; r < DP1; r++) out[e * DP1 + r] = xj[r];
+    }
+}
+__global__ void transform_from_kernel(const __grid_constant__ TrParams q, const double *__restrict__ x, int64_t total,
+                                      double *__restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = skd::from_pm1(q.tr[(int)(e % q.d)], x[e]);
+}
+
+cudaError_t transform_to(const sk_transform *tr, int d, int order, const double *y, int64_t n, double *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    TrParams q{};
+    q.d = d;
+    for (int j = 0; j < d; j++) q.tr[j] = tr[j];
+    int64_t total = n * d;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    switch (order) {
+    case 0: transform_to_kernel<1><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    case 1: transform_to_kernel<2><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    case 2: transform_to_kernel<3><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    case 3: transform_to_kernel<4><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    case 4: transform_to_kernel<5><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    case 5: transform_to_kernel<6><<<grid, 256, 0, stream>>>(q, y, total, out); break;
+    default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t transform_from(const sk_transform *tr, int d, const double *x, int64_t n, double *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    TrParams q{};
+    q.d = d;
+    for (int j = 0; j < d; j++) q.tr[j] = tr[j];
+    int64_t total = n * d;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    transform_from_kernel<<<grid, 256, 0, stream>>>(q, x, total, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------
+// FP64 pipe microbenchmarks: the roofline denominators MEASURED_PEAKS.json does not carry.
+//   which == 0: DFMA  — 16 independent fma chains per thread
+//   which == 1: DMMA  — mma.sync.aligned.m8n8k4.row.col.f64, 8 independent accumulator tiles/warp
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *sink) {
+    double a[16];
+    const double m = 1.0000001, c = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = 1.0 + i * 1e-3 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *sink) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t fp64_peak_launch(int which, int iters, double *sink, double *flops, cudaStream_t stream) {
+    int blocks = sm_count() * 8, threads = 256;
+    if (which == 0) {
+        dfma_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+        *flops = 2.0 * 16 * (double)iters * blocks * threads;
+    } else {
+        dmma_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+        *flops = 2.0 * 8 * 8 * 4 * 8 * (double)iters * blocks * (threads / 32);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace skk
+
+extern "C" int64_t sk_launch_count(void) { return skk::launch_count(); }

@@ -1,0 +1,40 @@
+// Kernel launchers (implemented in sk_kernels.cu / sk_nested.cu), called by the C-ABI layer.
+// All pointers are device pointers on the current device; all launches go to `stream`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sk_internal.h"
+
+namespace skk {
+
+// ---- univariate Chebyshev ∘ transformation
+cudaError_t uni_lincomb(int N, const sk_transform &tr, int order, bool exact, const double *theta, int nvec,
+                        const double *x, int64_t n, double *out, cudaStream_t stream);
+cudaError_t uni_basis_at(int N, const sk_transform &tr, int order, const double *x, int64_t n, double *out,
+                         int64_t ld, cudaStream_t stream);
+
+// ---- Smolyak, reference operation order (direct form, index table)
+cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
+                                   double *out, cudaStream_t stream);
+cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld,
+                                    cudaStream_t stream);
+
+// ---- Smolyak, nested run-structured evaluation (values, or value + full gradient)
+bool smolyak_nested_supported(const sk_plan &plan);
+cudaError_t smolyak_nested_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n,
+                                   double *out, cudaStream_t stream);
+// closed-form FP64 flop count per point of the nested kernel for this plan
+double smolyak_nested_flops(const sk_plan &plan);
+
+// ---- coordinate transformations over n×d points
+cudaError_t transform_to(const sk_transform *tr, int d, int order, const double *y, int64_t n, double *out,
+                         cudaStream_t stream);
+cudaError_t transform_from(const sk_transform *tr, int d, const double *x, int64_t n, double *out,
+                           cudaStream_t stream);
+
+// ---- FP64 pipe microbenchmarks; returns flops executed by one launch
+cudaError_t fp64_peak_launch(int which, int iters, double *sink, double *flops, cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+}  // namespace skk

@@ -1,0 +1,431 @@
+"""GPU parity tests: the CUDA library (through its C ABI / the Python mirror) against the CPU oracle.
+
+Parity bar (BASELINE.json north_star):
+  * exact mode (`exact=True`, and every basis_at / collocation_matrix / transform call) must be
+    BIT-IDENTICAL to the oracle, NaNs matching position for position;
+  * fast mode (fma-contracted, nested Smolyak evaluation) must satisfy
+        |gpu − oracle| ≤ TAU · S_r(x),   S_r(x) = Σ_k |θ_k|·|b_k^{(r)}(x)|   (oracle, absmode)
+    with TAU = 1e-13 for every derivative order r, away from the
+    transformation singularities (|x| ≤ 0.99 on the rational maps).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+
+pytestmark = pytest.mark.gpu
+
+sk = ge.load_package()
+TAU = 1e-13
+GRIDS = {0: sk.InteriorGrid(), 1: sk.EndpointGrid(), 2: sk.InteriorGrid2()}
+
+
+def same(a, b):
+    """bit-for-bit equality with NaNs matching"""
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def rand_pm1(rng, shape):
+    return np.clip((rng.random(shape) - 0.5) * 2.5, -1, 1)      # test/utilities.jl:28
+
+
+def mk_tr(orc, kind, a, b):
+    return ({1: sk.BoundedLinear, 2: sk.SemiInfRational, 3: sk.InfRational}[kind](a, b),
+            {1: orc.BoundedLinear, 2: orc.SemiInfRational, 3: orc.InfRational}[kind](a, b))
+
+
+MIXED6 = [(1, 0, 4), (1, -2, 2), (2, 1, 2), (3, 0, 4), (1, -1, 2), (2, -3, 3)]     # cfg 4b transformations
+
+
+# ------------------------------------------------------------------------------------------ univariate
+@pytest.mark.parametrize("N", [1, 2, 3, 20, 64, 128])
+@pytest.mark.parametrize("D", [0, 1, 2, 3, 5])
+def test_uni_bounded_linear_exact_and_fast(orc, N, D):
+    rng = np.random.default_rng(1000 * N + D)
+    t, ot = mk_tr(orc, 1, -2, 3)
+    theta = rng.standard_normal(N)
+    y = np.array([orc.transform_from(ot, u) for u in rand_pm1(rng, 1000)])
+    want = orc.uni_lincomb(N, theta, y, tr=ot, D=D)
+    basis = sk.Chebyshev(sk.InteriorGrid(), N) @ t
+    pts = (sk.d ** D)(y) if D else y
+    got = sk.linear_combination(basis, theta, pts, exact=True)
+    assert same(got.reshape(want.shape), want)
+    fast = sk.linear_combination(basis, theta, pts).reshape(want.shape)
+    scale = orc.uni_lincomb(N, theta, y, tr=ot, D=D, absmode=True)
+    assert np.max(np.abs(fast - want) / scale) <= TAU
+
+
+@pytest.mark.parametrize("kind,a,b", [(2, 0.7, 0.3), (3, 0.4, 0.9), (2, -3.0, -1.5)])
+@pytest.mark.parametrize("D", [0, 1, 2])
+def test_uni_rational_maps(orc, kind, a, b, D):
+    rng = np.random.default_rng(7 + D)
+    N = 128
+    t, ot = mk_tr(orc, kind, a, b)
+    theta = rng.standard_normal(N)
+    u = np.concatenate([rng.uniform(-0.99, 0.99, 2000), [0.0]])
+    y = np.array([orc.transform_from(ot, v) for v in u])
+    basis = sk.Chebyshev(sk.InteriorGrid(), N) @ t
+    pts = (sk.d ** D)(y) if D else y
+    if D == 2:      # the reference throws (transformations.jl:266,332); the extension is opt-in
+        with pytest.raises(sk.UnsupportedError):
+            sk.linear_combination(basis, theta, pts)
+    kw = dict(allow_rational_d2=True) if D == 2 else {}
+    want = orc.uni_lincomb(N, theta, y, tr=ot, D=D, ext2=True)
+    got = sk.linear_combination(basis, theta, pts, exact=True, **kw).reshape(want.shape)
+    assert same(got, want)
+    fast = sk.linear_combination(basis, theta, pts, **kw).reshape(want.shape)
+    scale = orc.uni_lincomb(N, theta, y, tr=ot, D=D, ext2=True, absmode=True)
+    assert np.max(np.abs(fast - want) / scale) <= TAU
+
+
+def test_uni_infinite_endpoints_exact_limits(orc):
+    # test/test_chebyshev.jl:109-146 through the batched path, both modes
+    N = 10
+    y = np.array([math.inf, -math.inf])
+    for t, minus in ((sk.SemiInfRational(2.3, 0.7), lambda i: 1.0), (sk.InfRational(0.3, 3.0), lambda i: (-1.0) ** (i + 1))):
+        basis = sk.Chebyshev(sk.InteriorGrid(), N) @ t
+        for i in range(1, N + 1):
+            theta = np.zeros(N)
+            theta[i - 1] = 1.0
+            for exact in (True, False):
+                out = sk.linear_combination(basis, theta, sk.d(y), exact=exact)
+                assert out[0, 0] == 1 and out[0, 1] == 0
+                assert out[1, 0] == minus(i) and out[1, 1] == 0
+
+
+def test_uni_endpoint_atoms_and_closed_forms(orc):
+    # test/test_chebyshev.jl:18-31: values/derivatives vs cos((n-1) acos x), incl. x = ±1
+    rng = np.random.default_rng(5)
+    for N in (5, 10):
+        x = rand_pm1(rng, 500)
+        theta = rng.random(N)
+        out = sk.linear_combination(sk.Chebyshev(sk.EndpointGrid(), N), theta, sk.d(x))
+        want = sum(theta[i] * np.cos(i * np.arccos(x)) for i in range(N))
+        np.testing.assert_allclose(out[:, 0], want, rtol=1e-10, atol=1e-12)
+        assert same(sk.linear_combination(sk.Chebyshev(sk.EndpointGrid(), N), theta, sk.d(x), exact=True),
+                    orc.uni_lincomb(N, theta, x, D=1))
+
+
+def test_uni_svector_coefficients(orc):
+    # test/test_generic_api.jl:95-102
+    rng = np.random.default_rng(13)
+    N, M = 10, 3
+    t, ot = mk_tr(orc, 2, 0.0, 1.0)
+    theta = rng.random((N, M))
+    x = rng.uniform(0.01, 30, 300)
+    basis = sk.Chebyshev(sk.InteriorGrid(), N) @ t
+    got = sk.linear_combination(basis, theta, x, exact=True)
+    assert same(got, orc.uni_lincomb(N, theta, x, tr=ot))
+    for v in range(M):
+        assert same(got[:, v], sk.linear_combination(basis, theta[:, v].copy(), x, exact=True))
+    fast = sk.linear_combination(basis, theta, x)
+    np.testing.assert_allclose(fast, got, rtol=1e-12, atol=1e-13)
+    theta = rng.standard_normal((64, 21))
+    got = sk.linear_combination(sk.Chebyshev(sk.InteriorGrid(), 64), theta, x / 30 - 0.5, exact=True)
+    assert same(got, orc.uni_lincomb(64, theta, x / 30 - 0.5))
+    with pytest.raises(sk.UnsupportedError):
+        sk.linear_combination(basis, theta[:10], sk.d(x))
+
+
+@pytest.mark.parametrize("n", [1, 20, 127, 128, 129, 1000])
+@pytest.mark.parametrize("D", [0, 1, 2])
+def test_uni_basis_at_bit_identical(orc, n, D):
+    # generic_api.jl:217-227; odd n exercises the unaligned (plain store) path, n >= 128 the bulk-copy path
+    rng = np.random.default_rng(n + D)
+    t, ot = mk_tr(orc, 1, -2, 3)
+    y = rng.uniform(-2, 3, n)
+    for N in (1, 20, 33):
+        want = orc.uni_basis_at(N, y, tr=ot, D=D)                          # (N, n, D+1)
+        got = sk.basis_at(sk.Chebyshev(sk.InteriorGrid(), N) @ t, (sk.d ** D)(y) if D else y)
+        assert same(np.asarray(got).reshape(n, N, D + 1), want.transpose(1, 0, 2))
+
+
+def test_collocation_default_grid_and_fit(orc):
+    # test/test_generic_api.jl:6-23
+    basis = sk.Chebyshev(sk.EndpointGrid(), 10)
+    assert same(sk.collocation_matrix(basis), sk.collocation_matrix(basis, sk.grid(basis)))
+    x = sk.grid(sk.Chebyshev(sk.EndpointGrid(), 20))
+    Cm = sk.collocation_matrix(basis, x)
+    assert Cm.shape == (20, 10) and np.isfinite(Cm).all()
+    phi = np.linalg.lstsq(Cm, np.exp(x), rcond=None)[0]
+    yy = np.linspace(-1, 1, 50)
+    assert np.max(np.abs(np.exp(yy) - sk.linear_combination(basis, phi, yy))) <= 1e-9
+    # cfg 1 of BASELINE.json: Chebyshev(InteriorGrid(), 20) collocation at its own grid
+    b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
+    assert same(sk.collocation_matrix(b20), orc.uni_basis_at(20, orc.cheb_grid(0, 20))[:, :, 0].T)
+
+
+def test_length_checks_and_errors():
+    # test/test_generic_api.jl:25-30; generic_api.jl:99-102
+    basis = sk.Chebyshev(sk.InteriorGrid(), 5)
+    with pytest.raises(sk.ArgumentError, match="too many coefficients"):
+        sk.linear_combination(basis, np.zeros(6), 0.0)
+    with pytest.raises(sk.ArgumentError, match="not enough coefficients"):
+        sk.linear_combination(basis, np.zeros(4), 0.0)
+    sb = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(2), 2)
+    with pytest.raises(sk.ArgumentError):
+        sk.linear_combination(sb, np.zeros(sk.dimension(sb)), np.zeros(3))          # smolyak_api.jl:97
+    with pytest.raises(sk.ArgumentError, match="too many coefficients"):
+        sk.linear_combination(sb, np.zeros(sk.dimension(sb) + 1), np.zeros(2))
+    with pytest.raises(sk.UnsupportedError):                                         # transformations.jl:266
+        sk.linear_combination(sb @ sk.coordinate_transformations(sk.SemiInfRational(0, 1), sk.BoundedLinear(0, 1)),
+                              np.zeros(sk.dimension(sb)), sk.partial(2)(np.ones(2)))
+    assert sk.linear_combination(basis, np.ones(5), 0.3).shape == ()                 # single point -> scalar
+
+
+def test_transformed_basis_equalities(orc):
+    # test/test_generic_api.jl:32-51,62-82: l1(transform_to(x)) == l2(x) == l3(x) with `==`
+    rng = np.random.default_rng(9)
+    basis = sk.Chebyshev(sk.EndpointGrid(), 10)
+    t = sk.BoundedLinear(1.0, 2.0)
+    theta = rng.standard_normal(10)
+    x = rng.random(20) + 1.0
+    l1 = sk.linear_combination(basis, theta)
+    l2 = sk.linear_combination(basis @ t, theta)
+    l3 = sk.linear_combination(basis, theta) @ t
+    assert same(l1(sk.transform_to(sk.domain(basis), t, x), exact=True), l2(x, exact=True))
+    assert same(l2(x, exact=True), l3(x, exact=True))
+    b0 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(2, 2), 2)
+    ct = sk.coordinate_transformations(sk.BoundedLinear(1.0, 2.0), sk.SemiInfRational(0, 1))
+    theta = rng.standard_normal(sk.dimension(b0))
+    x = rng.random((20, 2)) + 1.0
+    l1 = sk.linear_combination(b0, theta)
+    l2 = sk.linear_combination(b0 @ ct, theta)
+    assert same(l1(sk.transform_to(sk.domain(b0), ct, x), exact=True), l2(x, exact=True))
+    assert same(sk.grid(b0 @ ct), sk.transform_from(sk.domain(b0), ct, sk.grid(b0)))
+
+
+def test_batched_transforms_bit_identical(orc):
+    rng = np.random.default_rng(21)
+    pairs = [mk_tr(orc, *k) for k in MIXED6]
+    ct = sk.coordinate_transformations(*[p[0] for p in pairs])
+    otr = [p[1] for p in pairs]
+    u = rand_pm1(rng, (4000, 6))
+    with np.errstate(all="ignore"):
+        y = sk.transform_from(None, ct, u)
+        assert same(y, orc.transform_from_batch(otr, u))
+        y = np.where(np.isnan(y), 0.5, y)
+        assert same(sk.transform_to(None, ct, y), orc.transform_to_batch(otr, y)[:, :, 0])
+        assert same(sk.transform_to(None, ct, sk.d(y)), orc.transform_to_batch(otr, y, D=1))
+    # docstring known answer, transformations.jl:88-104
+    ct2 = sk.coordinate_transformations(sk.BoundedLinear(0, 2), sk.SemiInfRational(2, 3))
+    x = sk.transform_from(None, ct2, np.array([0.4, 0.5]))
+    assert x.tolist() == [1.4, 11.0]
+    assert sk.transform_to(None, ct2, x).tolist() == [0.3999999999999999, 0.5]
+    # ±Inf limits, test/test_transformations.jl:50-57,85-92
+    for t, vals in ((sk.SemiInfRational(3.0, 4.0), (1.0, 1.0)), (sk.InfRational(0.0, 1.0), (1.0, -1.0))):
+        out = sk.transform_to(None, t, sk.d(np.array([math.inf, -math.inf])))
+        assert out[:, 0].tolist() == list(vals) and out[:, 1].tolist() == [0.0, 0.0]
+
+
+# ------------------------------------------------------------------------------------------ Smolyak
+SMOLYAK_CASES = [(0, 2, 3, 3), (1, 3, 3, 2), (2, 3, 4, 4), (2, 6, 2, 2), (1, 4, 3, 3), (0, 3, 2, 1), (2, 1, 4, 4), (2, 2, 0, 0)]
+
+
+@pytest.mark.parametrize("code,d,B,M", SMOLYAK_CASES)
+def test_smolyak_exact_bit_identical(orc, code, d, B, M):
+    rng = np.random.default_rng(code * 100 + d * 10 + B)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B, M), d)
+    K = sk.dimension(basis)
+    theta = rng.standard_normal(K)
+    x = rand_pm1(rng, (300, d))
+    assert same(sk.linear_combination(basis, theta, x, exact=True), orc.smolyak_lincomb(code, d, B, M, theta, x)[:, 0])
+    spec, ospec = sk.gradient(d), orc.gradient_spec(d)
+    assert same(sk.linear_combination(basis, theta, spec(x), exact=True),
+                orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec))
+    if d >= 2:
+        spec = sk.partial(1, 1) | sk.partial(0, 2)
+        ospec = orc.deriv_spec([(1, 1), (0, 2)], d)
+        assert same(sk.linear_combination(basis, theta, spec(x), exact=True),
+                    orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec))
+
+
+@pytest.mark.parametrize("code,d,B,M", SMOLYAK_CASES + [(2, 6, 4, 4), (1, 8, 3, 3), (0, 5, 3, 3), (2, 10, 3, 3), (2, 4, 5, 5)])
+def test_smolyak_fast_within_tolerance(orc, code, d, B, M):
+    rng = np.random.default_rng(code * 100 + d * 10 + B + 1)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B, M), d)
+    assert sk.get_plan(basis).info.fast_path == 1
+    K = sk.dimension(basis)
+    theta = rng.standard_normal(K)
+    n = 2000 if K < 5000 else 300
+    x = rand_pm1(rng, (n, d))
+    want = orc.smolyak_lincomb(code, d, B, M, theta, x)[:, 0]
+    scale = orc.smolyak_lincomb(code, d, B, M, theta, x, absmode=True)[:, 0]
+    got = sk.linear_combination(basis, theta, x)
+    assert np.max(np.abs(got - want) / scale) <= TAU
+    ospec = orc.gradient_spec(d)
+    want = orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec)
+    scale = orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec, absmode=True)
+    got = sk.linear_combination(basis, theta, sk.gradient(d)(x))
+    assert got.shape == (n, d + 1)
+    assert np.max(np.abs(got - want) / scale) <= TAU
+
+
+def test_smolyak_headline_config_with_transformations(orc):
+    # BASELINE cfg 4b: d=6, B=4, InteriorGrid2, mixed transformations, value + gradient
+    rng = np.random.default_rng(104)
+    d, B = 6, 4
+    pairs = [mk_tr(orc, *k) for k in MIXED6]
+    ct = sk.coordinate_transformations(*[p[0] for p in pairs])
+    otr = [p[1] for p in pairs]
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d) @ ct
+    K = sk.dimension(basis)
+    assert K == 2561
+    theta = rng.standard_normal(K)
+    y = orc.transform_from_batch(otr, rng.uniform(-0.99, 0.99, (1500, d)))
+    ospec = orc.gradient_spec(d)
+    want = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec)
+    scale = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec, absmode=True)
+    assert same(sk.linear_combination(basis, theta, sk.gradient(d)(y), exact=True), want)
+    got = sk.linear_combination(basis, theta, sk.gradient(d)(y))
+    assert np.max(np.abs(got - want) / scale) <= TAU
+    info = sk.get_plan(basis, 0, sk.gradient(d)).info
+    assert info.fast_path == 1 and info.K == 2561 and info.H == 31 and info.n_runs == 1471 and info.E == 7
+    assert info.flops_per_point_direct == 126569.0                        # SURVEY.md §8(d) F_direct
+    # ±Inf on the rational coordinates: finite results, value/gradient limits exact in both modes
+    yinf = y[:8].copy()
+    yinf[:, 2] = math.inf
+    yinf[:, 3] = -math.inf
+    w = orc.smolyak_lincomb(2, d, B, B, theta, yinf, trs=otr, spec=ospec)
+    assert same(sk.linear_combination(basis, theta, sk.gradient(d)(yinf), exact=True), w)
+    g = sk.linear_combination(basis, theta, sk.gradient(d)(yinf))
+    assert np.isfinite(g).all() and (g[:, 3] == 0).all() and (g[:, 4] == 0).all()
+
+
+def test_smolyak_gradient_correctness_vs_analytic(orc):
+    # the reference never checks multivariate derivative values (test/test_smolyak.jl:32-42): do it here.
+    # Fit f(x) = (x1 - 3)(x2 + 5) exactly (test/test_smolyak.jl:13-30), then compare the gradient analytically.
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(3), 2)
+    g = sk.grid(basis)
+    Cm = sk.collocation_matrix(basis, g)
+    theta = np.linalg.solve(Cm, (g[:, 0] - 3) * (g[:, 1] + 5))
+    assert int((np.abs(theta) > 1e-8).sum()) == 4
+    yy = np.stack(np.meshgrid(np.linspace(-1, 1, 100), np.linspace(-1, 1, 100)), -1).reshape(-1, 2)
+    out = sk.linear_combination(basis, theta, sk.gradient(2)(yy))
+    np.testing.assert_allclose(out[:, 0], (yy[:, 0] - 3) * (yy[:, 1] + 5), rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out[:, 1], yy[:, 1] + 5, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(out[:, 2], yy[:, 0] - 3, rtol=1e-10, atol=1e-10)
+    full = sk.linear_combination(basis, theta, sk.partial(1, 1)(yy), exact=True)       # ∂(1,1): [f, ∂1, ∂2, ∂1∂2]
+    np.testing.assert_allclose(full[:, 3], 1.0, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 200])
+def test_smolyak_basis_at_bit_identical(orc, n):
+    rng = np.random.default_rng(n)
+    for code, d, B, M in [(2, 3, 3, 3), (0, 2, 3, 3), (1, 4, 2, 2)]:
+        basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B, M), d)
+        x = rand_pm1(rng, (n, d))
+        K = sk.dimension(basis)
+        want = orc.smolyak_basis_at(code, d, B, M, x)                                  # (K, n, 1)
+        assert same(np.asarray(sk.basis_at(basis, x)), want[:, :, 0].T)
+        ospec = orc.gradient_spec(d)
+        want = orc.smolyak_basis_at(code, d, B, M, x, spec=ospec)
+        got = np.asarray(sk.basis_at(basis, sk.gradient(d)(x)))
+        assert got.shape == (n, K, d + 1) and same(got, want.transpose(1, 0, 2))
+
+
+def test_smolyak_collocation_at_own_grid(orc):
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 3)
+    Cm = sk.collocation_matrix(basis)
+    K = sk.dimension(basis)
+    assert Cm.shape == (K, K)
+    assert same(Cm, orc.smolyak_basis_at(2, 3, 3, 3, orc.smolyak_grid(2, 3, 3, 3))[:, :, 0].T)
+    assert np.linalg.cond(Cm) < 1e6
+
+
+def test_smolyak_svector_coefficients(orc):
+    rng = np.random.default_rng(33)
+    d, B = 4, 3
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    K = sk.dimension(basis)
+    theta = rng.standard_normal((K, 11))
+    x = rng.uniform(-1, 1, (100, d))
+    got = sk.linear_combination(basis, theta, x, exact=True)
+    assert same(got, orc.smolyak_lincomb(2, d, B, B, theta, x))
+    for v in (0, 10):
+        assert same(got[:, v], sk.linear_combination(basis, theta[:, v].copy(), x, exact=True))
+
+
+def test_golden_fixtures(orc):
+    g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
+    b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
+    assert same(sk.linear_combination(b20, g["c1_theta"], g["c1_x"], exact=True), g["c1_val"])
+    assert same(sk.collocation_matrix(b20), g["c1_colloc"])
+    b64 = sk.Chebyshev(sk.InteriorGrid(), 64) @ sk.BoundedLinear(-2, 3)
+    assert same(sk.linear_combination(b64, g["c2_theta"], sk.d(g["c2_y"]), exact=True), g["c2_out"])
+    for name, t in (("semi", sk.SemiInfRational(0.7, 0.3)), ("inf", sk.InfRational(0.4, 0.9))):
+        b128 = sk.Chebyshev(sk.InteriorGrid(), 128) @ t
+        assert same(sk.linear_combination(b128, g["c3_theta"], sk.d(g[f"c3_{name}_y"]), exact=True), g[f"c3_{name}_d1"])
+        assert same(sk.linear_combination(b128, g["c3_theta"], (sk.d ** 2)(g[f"c3_{name}_y"]), exact=True,
+                                          allow_rational_d2=True), g[f"c3_{name}_d2"])
+    ct = sk.coordinate_transformations(sk.BoundedLinear(0, 4), sk.SemiInfRational(1, 2), sk.InfRational(0, 4), sk.SemiInfRational(-3, 3))
+    b4 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 4)
+    assert same(sk.linear_combination(b4 @ ct, g["c4_theta"], sk.gradient(4)(g["c4_y"]), exact=True), g["c4_grad"])
+    assert same(sk.linear_combination(b4 @ ct, g["c4_theta"], g["c4_y"], exact=True), g["c4_val"])
+    np.testing.assert_allclose(sk.linear_combination(b4 @ ct, g["c4_theta"], sk.gradient(4)(g["c4_y"])), g["c4_grad"], rtol=1e-11, atol=1e-11)
+    assert same(sk.linear_combination(b4, g["c5_theta"], g["c5_y"], exact=True), g["c5_out"])
+
+
+def test_device_pointers_and_sharded_driver(orc):
+    import torch
+    rng = np.random.default_rng(55)
+    d, B = 6, 4
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    theta = rng.standard_normal(sk.dimension(basis))
+    x = rng.uniform(-1, 1, (5000, d))
+    host = sk.linear_combination(basis, theta, sk.gradient(d)(x))
+    dev = sk.linear_combination(basis, torch.as_tensor(theta).cuda(), sk.gradient(d)(torch.as_tensor(x).cuda()))
+    assert dev.is_cuda and same(dev.cpu().numpy(), host)
+    sh = sk.linear_combination_sharded(basis, theta, sk.gradient(d)(x), devices=list(range(torch.cuda.device_count())))
+    assert same(sh, host)
+    Bm = sk.basis_at(basis, torch.as_tensor(x[:64]).cuda())
+    assert same(Bm.cpu().numpy(), np.asarray(sk.basis_at(basis, x[:64])))
+
+
+def test_large_host_batch_goes_through_the_chunk_pipeline(orc):
+    # > 2^22 points: the host path double-buffers chunks; results must not depend on chunking
+    rng = np.random.default_rng(77)
+    N = 16
+    t, ot = mk_tr(orc, 1, -2, 3)
+    theta = rng.standard_normal(N)
+    n = (1 << 22) * 2 + 12345
+    y = rng.uniform(-2, 3, n)
+    got = sk.linear_combination(sk.Chebyshev(sk.InteriorGrid(), N) @ t, theta, sk.d(y), exact=True)
+    sel = np.concatenate([np.arange(0, 1000), np.arange((1 << 22) - 500, (1 << 22) + 500), np.arange(n - 1000, n)])
+    assert same(got[sel], orc.uni_lincomb(N, theta, y[sel], tr=ot, D=1))
+
+
+def test_full_size_headline_properties(orc):
+    # BASELINE cfg 4 at its full size (10^8 points, device resident): properties that do not need the
+    # oracle on every point — linearity in θ, and a strided subsample against the oracle.
+    import torch
+    n = int(os.environ.get("SK_FULL_N", 100_000_000))
+    d, B = 6, 4
+    pairs = [mk_tr(orc, *k) for k in MIXED6]
+    ct = sk.coordinate_transformations(*[p[0] for p in pairs])
+    otr = [p[1] for p in pairs]
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d) @ ct
+    gen = torch.Generator(device="cuda").manual_seed(104)
+    u = torch.rand((n, d), generator=gen, device="cuda", dtype=torch.float64) * 1.98 - 0.99
+    y = sk.transform_from(None, ct, u)
+    del u
+    rng = np.random.default_rng(4)
+    th1, th2 = rng.standard_normal(2561), rng.standard_normal(2561)
+    spec = sk.gradient(d)
+    o1 = sk.linear_combination(basis, torch.as_tensor(th1).cuda(), spec(y))
+    o2 = sk.linear_combination(basis, torch.as_tensor(th2).cuda(), spec(y))
+    o12 = sk.linear_combination(basis, torch.as_tensor(th1 + th2).cuda(), spec(y))
+    assert torch.isfinite(o12).all()
+    lin = (o12 - (o1 + o2)).abs().amax(dim=0).cpu().numpy()
+    ref = (o1.abs() + o2.abs()).amax(dim=0).cpu().numpy()
+    assert (lin <= 1e-9 * ref).all(), (lin, ref)
+    sel = torch.arange(0, n, max(1, n // 1500), device="cuda")
+    ys = y[sel].cpu().numpy()
+    ospec = orc.gradient_spec(d)
+    want = orc.smolyak_lincomb(2, d, B, B, th1, ys, trs=otr, spec=ospec)
+    scale = orc.smolyak_lincomb(2, d, B, B, th1, ys, trs=otr, spec=ospec, absmode=True)
+    assert np.max(np.abs(o1[sel].cpu().numpy() - want) / scale) <= TAU

@@ -1,0 +1,211 @@
+"""CPU-side checks of the product library: it loads, exports the whole C ABI, fails loudly without a
+GPU, and its host plan builder (integers + grids) is BIT-EXACT against the oracle."""
+import ctypes
+import itertools
+import math
+import re
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+
+sk = ge.load_package()
+GRIDS = [(sk.InteriorGrid(), 0), (sk.EndpointGrid(), 1), (sk.InteriorGrid2(), 2)]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ge.ROOT, "include", "spectralkit_b200.h")).read()
+    declared = set(re.findall(r"\b(sk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(sk._lib.EXPORTS)
+    lib = ctypes.CDLL(sk._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert "sm_100a" in sk._lib.lib.sk_version().decode()
+
+
+def test_library_contains_only_sm100a_code():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", sk._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    basis = sk.Chebyshev(sk.InteriorGrid(), 5)
+    with pytest.raises(sk.CudaError):
+        sk.linear_combination(basis, np.zeros(5), np.zeros(3))
+    with pytest.raises(sk.CudaError):
+        sk.basis_at(basis, np.zeros(3))
+    with pytest.raises(sk.CudaError):
+        sk.transform_to(None, sk.BoundedLinear(0, 1), np.zeros(3))
+
+
+def test_nesting_lengths(orc):
+    for g, code in GRIDS:
+        for b in range(0, 8):
+            assert sk.nesting_total_length(g, b) == orc.nesting_total_length(code, b)
+            assert sk.nesting_block_length(g, b) == orc.nesting_block_length(code, b)
+
+
+def test_grid_shuffle_bit_exact(orc):
+    # closed-form shuffle (product) vs the reference's iterator state machines (oracle)
+    for g, code in GRIDS:
+        for b in range(0, 8):
+            n = orc.nesting_total_length(code, b)
+            assert sk.grid_shuffle(g, n).tolist() == orc.grid_shuffle(code, n).tolist(), (code, b)
+        with pytest.raises(sk.ArgumentError):
+            sk.grid_shuffle(g, 4)
+
+
+@pytest.mark.parametrize("g,code", GRIDS)
+def test_smolyak_indices_bit_exact(orc, g, code):
+    # constrained odometer (product) vs `__inc` state machine (oracle): identical tuples, identical order
+    cases = [(d, B, M) for B in range(0, 5) for M in range(0, B + 1) for d in range(1, 5)]
+    cases += [(6, 4, 4), (6, 4, 2), (5, 5, 3), (10, 3, 3), (7, 2, 5)]
+    for d, B, M in cases:
+        K = orc.smolyak_length(code, d, B, M)
+        if K > 60000:
+            continue
+        basis = sk.smolyak_basis(sk.Chebyshev, g, _params(B, M), d)
+        assert sk.dimension(basis) == K
+        assert basis.univariate_parent.N == orc.smolyak_parent_dimension(code, B, M)
+        assert (sk.smolyak_indices(basis) == orc.smolyak_indices(code, d, B, M)).all(), (code, d, B, M)
+
+
+def _params(B, M):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return sk.SmolyakParameters(B, M)
+
+
+def test_smolyak_indices_golden_naive_filter():
+    # fixtures from the naive filtered Cartesian enumeration (test/test_smolyak_traversal.jl:74-90)
+    gold = np.load(os.path.join(ge.ROOT, "tests", "golden", "indices.npz"))
+    for key in gold.files:
+        code, d, B, M = [int(v[1:]) for v in key.split("_")]
+        g = [g for g, c in GRIDS if c == code][0]
+        basis = sk.smolyak_basis(sk.Chebyshev, g, _params(B, M), d)
+        assert (sk.smolyak_indices(basis) == gold[key]).all(), key
+
+
+def test_headline_sizes():
+    b4 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), 6)
+    assert sk.dimension(b4) == 2561 and b4.univariate_parent.N == 31
+    b5 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(5), 10)
+    assert sk.dimension(b5) == 77505 and b5.univariate_parent.N == 63
+    # docstring example smolyak_api.jl:46-49
+    b = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(3), 2)
+    assert sk.dimension(b) == 81 and b.univariate_parent.N == 27
+
+
+def test_smolyak_parameters_warning():
+    with pytest.warns(UserWarning, match="M > B replaced with M = B"):
+        p = sk.SmolyakParameters(2, 4)
+    assert (p.B, p.M) == (2, 2)
+
+
+@pytest.mark.parametrize("g,code", GRIDS)
+def test_grids_bit_exact(orc, g, code):
+    for N in [1, 2, 3, 5, 7, 9, 15, 17, 20, 27, 31, 33, 63, 64, 65, 81, 127, 128, 243]:
+        assert sk.grid(sk.Chebyshev(g, N)).tolist() == orc.cheb_grid(code, N).tolist(), (code, N)
+    t, ot = sk.SemiInfRational(0.7, 0.3), orc.SemiInfRational(0.7, 0.3)
+    with np.errstate(all="ignore"):
+        assert sk.grid(sk.Chebyshev(g, 20) @ t).tolist() == orc.cheb_grid(code, 20, tr=ot).tolist()
+    for d, B, M in [(2, 3, 3), (3, 3, 2), (6, 4, 4), (4, 5, 3)]:
+        if orc.smolyak_length(code, d, B, M) > 60000:
+            continue
+        basis = sk.smolyak_basis(sk.Chebyshev, g, _params(B, M), d)
+        assert (sk.grid(basis) == orc.smolyak_grid(code, d, B, M)).all()
+    basis = sk.smolyak_basis(sk.Chebyshev, g, sk.SmolyakParameters(3), 3)
+    ct = sk.coordinate_transformations(sk.BoundedLinear(0, 4), sk.SemiInfRational(1, 2), sk.InfRational(0, 4))
+    otr = [orc.BoundedLinear(0, 4), orc.SemiInfRational(1, 2), orc.InfRational(0, 4)]
+    with np.errstate(all="ignore"):
+        got, want = sk.grid(basis @ ct), orc.smolyak_grid(code, 3, 3, 3, trs=otr)
+    assert ((got == want) | (np.isnan(got) & np.isnan(want))).all()
+
+
+def test_grid_golden_mpmath():
+    # correctly rounded sinpi/cospi pinned by 240-bit mpmath (tests/golden/make_golden.py)
+    gold = np.load(os.path.join(ge.ROOT, "tests", "golden", "grids.npz"))
+    for g, code in GRIDS:
+        for N in (20, 31, 63, 128, 243):
+            assert sk.grid(sk.Chebyshev(g, N)).tolist() == gold[f"g{code}_N{N}"].tolist()
+
+
+def test_partials_algebra_matches_oracle(orc):
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        dim = int(rng.integers(1, 5))
+        specs = []
+        for _ in range(int(rng.integers(1, 4))):
+            ln = int(rng.integers(1, dim + 1))
+            p = [int(v) for v in rng.integers(0, 3, ln)]
+            specs.append(tuple(p))
+        spec = sk.partial(*specs[0])
+        for p in specs[1:]:
+            spec = spec | sk.partial(*p)
+        try:
+            want = orc.deriv_spec(specs, dim)
+        except orc.OracleError:
+            continue
+        if len(want) > 64:
+            continue
+        table, deg = spec.expansion(dim)
+        assert table.tolist() == want.tolist(), specs
+        assert deg.tolist() == orc.partials_degrees(orc.partials_minimal(specs, dim), dim).tolist()
+    assert sk.gradient(6).expansion(6)[0].tolist() == orc.gradient_spec(6).tolist()
+
+
+def test_transformation_constructors():
+    # test/test_transformations.jl:4-5,27-29,61-64
+    for ctor, args in [(sk.BoundedLinear, (-1.0, math.inf)), (sk.BoundedLinear, (-1.0, -2.0)),
+                       (sk.SemiInfRational, (-1.0, math.inf)), (sk.SemiInfRational, (-1.0, 0.0)),
+                       (sk.SemiInfRational, (math.nan, 2.0)), (sk.InfRational, (1.0, math.inf)),
+                       (sk.InfRational, (1.0, 0.0)), (sk.InfRational, (1.0, -2.0)), (sk.InfRational, (math.nan, 1))]:
+        with pytest.raises(sk.DomainError):
+            ctor(*args)
+    t = sk.BoundedLinear(1, 5)
+    assert (t.m, t.s) == (3.0, 2.0) and sk.extrema(sk.domain(t)) == (1.0, 5.0)
+    assert sk.extrema(sk.domain(sk.SemiInfRational(3.0, 4.0))) == (3.0, math.inf)
+    assert sk.extrema(sk.domain(sk.InfRational(0.0, 1.0))) == (-math.inf, math.inf)
+    # test/test_transformations.jl:113-127 reprs
+    assert repr(sk.BoundedLinear(2.0, 3)) == "(2.0,3.0) ↔ domain [linear transformation]"
+    assert repr(sk.SemiInfRational(7.0, 1)) == "(7.0,∞) ↔ domain [rational transformation with scale 1.0]"
+    assert repr(sk.InfRational(0.5, 1)) == "(-∞,∞) ↔ domain [rational transformation with center 0.5, scale 1.0]"
+
+
+def test_basis_constructors_and_api_surface():
+    with pytest.raises(sk.ArgumentError):
+        sk.Chebyshev(sk.InteriorGrid(), 0)                                    # test/test_chebyshev.jl:6-7
+    with pytest.raises(TypeError):
+        sk.Chebyshev("invalid_grid", 10)                                      # :8
+    with pytest.raises(TypeError):
+        sk.smolyak_basis(sk.Chebyshev, "invalid_grid", sk.SmolyakParameters(3), 2)   # test/test_smolyak.jl:9
+    basis = sk.Chebyshev(sk.EndpointGrid(), 10)
+    t = sk.BoundedLinear(1.0, 2.0)
+    tb = basis @ t
+    assert sk.is_function_basis(tb) and sk.is_function_basis(sk.Chebyshev) and not sk.is_function_basis("a fish")
+    assert sk.domain(tb) == sk.domain(t) and sk.dimension(tb) == 10 and sk.parent(tb) is basis and sk.transformation(tb) is t
+    assert sk.transformation(basis) is None
+    b0 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(2, 2), 2)
+    ct = sk.coordinate_transformations(sk.BoundedLinear(1.0, 2.0), sk.SemiInfRational(0, 1))
+    b = b0 @ ct
+    assert len(b) == 2 and b[2] == b0.univariate_parent @ ct.transformations[1]   # test/test_generic_api.jl:70
+    with pytest.raises(IndexError):
+        b0[3]
+    with pytest.raises(sk.ArgumentError):
+        b0 @ sk.coordinate_transformations(sk.BoundedLinear(1.0, 2.0))
+    with pytest.raises(sk.ArgumentError):
+        sk.linear_combination(basis, np.zeros(11))                            # test/test_generic_api.jl:29
+    # 𝑑 algebra: test/test_derivatives.jl:14-18
+    assert (sk.d * sk.d).D == 2 and (sk.d ** 3).D == 3 and ((sk.d ** 2) << 3).partials == ((0, 0, 2),)
+    assert repr(sk.partial(1, 2) | sk.partial(2, 1)) == "union(∂(1, 2), ∂(2, 1))"
+    assert sk.partial(1, 0).partials == ((1,),)
+    with pytest.raises(sk.ArgumentError):
+        sk.partial((1, 0))
