@@ -278,7 +278,8 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         double ftab = 0;
         for (int j = 0; j < d; j++) ftab += (double)(p->H - 1) * (p->deg[j] == 0 ? 2 : p->deg[j] == 1 ? 6 : 12);
         p->flops_direct = (double)p->K * (C * (d - 1) + 2 * C) + ftab;
-        p->flops_fast = skk::smolyak_nested_supported(*p) ? skk::smolyak_nested_flops(*p) : p->flops_direct;
+        p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
+        p->flops_fast = p->fast_kernel == 2 ? skk::smolyak_leaf_flops(*p) : p->fast_kernel == 1 ? skk::smolyak_nested_flops(*p) : p->flops_direct;
     }
     // the reference throws for order >= 2 through the rational maps (transformations.jl:266,332)
     for (int j = 0; j < d; j++)
@@ -293,6 +294,13 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         CK(cudaMemcpy(p->d_idx, p->set.idx.data(), p->set.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&p->d_runs, prog.size() * sizeof(uint32_t)));
         CK(cudaMemcpy(p->d_runs, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (p->fast_kernel == 2) {
+            std::vector<uint32_t> units;
+            skk::smolyak_leaf_units(*p, units);
+            p->n_units = (int64_t)units.size();
+            CK(cudaMalloc(&p->d_units, units.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
     }
     *out = p.release();
     return SK_OK;
@@ -304,6 +312,7 @@ int sk_plan_destroy(sk_plan *plan) {
         DeviceGuard g(plan->device);
         if (plan->d_idx) cudaFree(plan->d_idx);
         if (plan->d_runs) cudaFree(plan->d_runs);
+        if (plan->d_units) cudaFree(plan->d_units);
     }
     delete plan;
     return SK_OK;
@@ -316,7 +325,7 @@ int sk_plan_get_info(const sk_plan *plan, sk_plan_info *info) {
     info->d = plan->basis.kind == SK_BASIS_CHEBYSHEV ? 1 : plan->basis.d;
     info->B = plan->basis.B; info->M = plan->basis.M; info->device = plan->device;
     info->K = plan->K; info->H = plan->H; info->E = plan->E;
-    info->fast_path = plan->basis.kind == SK_BASIS_CHEBYSHEV ? 1 : (skk::smolyak_nested_supported(*plan) ? 1 : 0);
+    info->fast_path = plan->basis.kind == SK_BASIS_CHEBYSHEV ? 1 : plan->fast_kernel;
     info->n_runs = plan->n_runs;
     info->flops_per_point_fast = plan->flops_fast;
     info->flops_per_point_direct = plan->flops_direct;
@@ -334,7 +343,11 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         CK(skk::uni_lincomb(plan->basis.N, plan->tr[0], plan->order, exact, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
-    if (!exact && nvec == 1 && skk::smolyak_nested_supported(*plan)) {
+    if (!exact && nvec == 1 && plan->fast_kernel == 2) {
+        CK(skk::smolyak_leaf_lincomb(*plan, d_theta, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    if (!exact && nvec == 1 && plan->fast_kernel == 1) {
         CK(skk::smolyak_nested_lincomb(*plan, d_theta, d_x, n, d_out, stream));
         return SK_OK;
     }

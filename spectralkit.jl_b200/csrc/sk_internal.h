@@ -66,7 +66,10 @@ struct sk_plan {
     skh::SmolyakSet set;
     // device tables (Smolyak)
     uint16_t *d_idx = nullptr;   // [K][d]
-    uint32_t *d_runs = nullptr;  // [n_runs] run_len | carry << 24
+    uint32_t *d_runs = nullptr;  // [n_runs] run_len | carry << 24   (generic nested kernel)
     int64_t n_runs = 0;
+    uint32_t *d_units = nullptr; // [n_units] r | carry << 8             (unrolled-leaf kernel)
+    int64_t n_units = 0;
+    int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves
     double flops_fast = 0, flops_direct = 0;
 };

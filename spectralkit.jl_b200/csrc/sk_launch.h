@@ -26,6 +26,13 @@ cudaError_t smolyak_nested_lincomb(const sk_plan &plan, const double *theta, con
 // closed-form FP64 flop count per point of the nested kernel for this plan
 double smolyak_nested_flops(const sk_plan &plan);
 
+// ---- Smolyak, nested evaluation with compile-time unrolled leaves (sk_leaf.cu): the headline kernel
+bool smolyak_leaf_supported(const sk_plan &plan);
+void smolyak_leaf_units(const sk_plan &plan, std::vector<uint32_t> &units);
+cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n,
+                                 double *out, cudaStream_t stream);
+double smolyak_leaf_flops(const sk_plan &plan);
+
 // ---- coordinate transformations over n×d points
 cudaError_t transform_to(const sk_transform *tr, int d, int order, const double *y, int64_t n, double *out,
                          cudaStream_t stream);

@@ -258,7 +258,7 @@ def test_smolyak_exact_bit_identical(orc, code, d, B, M):
 def test_smolyak_fast_within_tolerance(orc, code, d, B, M):
     rng = np.random.default_rng(code * 100 + d * 10 + B + 1)
     basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B, M), d)
-    assert sk.get_plan(basis).info.fast_path == 1
+    assert sk.get_plan(basis).info.fast_path >= 1
     K = sk.dimension(basis)
     theta = rng.standard_normal(K)
     n = 2000 if K < 5000 else 300
@@ -294,7 +294,7 @@ def test_smolyak_headline_config_with_transformations(orc):
     got = sk.linear_combination(basis, theta, sk.gradient(d)(y))
     assert within(got, want, scale)
     info = sk.get_plan(basis, 0, sk.gradient(d)).info
-    assert info.fast_path == 1 and info.K == 2561 and info.H == 31 and info.n_runs == 1471 and info.E == 7
+    assert info.fast_path >= 1 and info.K == 2561 and info.H == 31 and info.n_runs == 1471 and info.E == 7
     assert info.flops_per_point_direct == 126569.0                        # SURVEY.md §8(d) F_direct
     # ±Inf on the rational coordinates: finite results, value/gradient limits exact in both modes
     yinf = y[:8].copy()
