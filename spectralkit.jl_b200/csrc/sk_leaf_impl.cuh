@@ -1,0 +1,389 @@
+// sm_100a kernels, part 3 — K2 (headline): Smolyak linear_combination with compile-time unrolled
+// leaves.  Same nested (Horner-like) evaluation as sk_nested.cu, restructured so that the FP64
+// pipe, not instruction issue, is the limit:
+//
+//   * The lowest LL (<= 6) dimensions of the index set are a "leaf": for a remaining block budget
+//     r, the set {(i_1..i_LL) : Σ b_j <= r} is FIXED, so Leaf<GK, LL, r> is straight-line code
+//     produced by template recursion over the block structure of the nested family GK
+//     (smolyak_traversal.jl:69-84,112-116,146-148).  No index table, no state machine, no branch:
+//     every fma has register operands and a θ read at a compile-time offset from the unit's base.
+//     For d <= 6 the whole evaluation of a point is one straight-line leaf.
+//   * Chebyshev values/derivatives for indices 2..7 (degrees 1..6: blocks 0-2 of all three
+//     families) are per-point tables: in REGISTERS for the lowest TREG dimensions (where almost all
+//     nodes are), in shared memory ([entry][thread] double2 = (T, T'), conflict-free LDS.128) for
+//     the rest.  Higher indices continue the three-term recurrence in registers.
+//   * Index 1 is T_0 = 1, T_0' = 0: the first child of every node is a register rename.
+//   * Dimensions above LL (d > 6, or budgets without pre-built leaf code) are walked by a small
+//     uniform interpreter over a unit program (one word per distinct tail (i_{LL+1}..i_d)); its
+//     per-level state lives in shared memory, touched once per unit.
+//   * θ and the unit program are staged in shared memory once per CTA (θ reads are broadcasts);
+//     CTAs are persistent (grid = SMs × resident CTAs).
+//
+// Reference semantics reproduced (within tolerance; the summation order differs and fma is used):
+// smolyak_api.jl:89-110, smolyak_traversal.jl:373-379, derivatives.jl:502-511, generic_api.jl:114-128.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+
+#include "sk_device.cuh"
+#include "sk_launch.h"
+
+namespace skk {
+
+// ---- block structure at compile time
+template <int GK>
+__host__ __device__ constexpr int ellc(int b) {
+    if (GK == SK_GRID_ENDPOINT) return b == 0 ? 1 : (1 << b) + 1;
+    if (GK == SK_GRID_INTERIOR) { int r = 1; for (int i = 0; i < b; i++) r *= 3; return r; }
+    return (1 << (b + 1)) - 1;
+}
+template <int GK>
+__host__ __device__ constexpr int blockof(int i) {
+    int b = 0;
+    while (ellc<GK>(b) < i) b++;
+    return b;
+}
+
+constexpr int kTab = 6;              // table entries: indices 2..7 (degrees 1..6)
+constexpr int kLeafThreads = 128;
+#ifndef SK_TREG
+#define SK_TREG 3                    // dimensions whose table lives in registers
+#endif
+
+template <bool GRAD>
+struct DimTab {
+    double t[kTab];
+    double dt[GRAD ? kTab : 1];
+    double x2, x2d;
+};
+
+// per-thread evaluation context; the type carries the compile-time configuration
+template <bool GRAD_, int TREG_, int FENCE_>
+struct LeafCtx {
+    static constexpr bool GRAD = GRAD_;
+    static constexpr int TREG = TREG_;      // dimensions with register tables
+    static constexpr int FENCE = FENCE_;    // sub-leaves of this many dimensions are separated by a scheduling
+                                            // fence (keeps ptxas from interleaving too many subtrees); 0 = none
+    DimTab<GRAD_> tabs[TREG_ > 0 ? TREG_ : 1];
+    const double2 *stab;                    // shared tables of dims >= TREG, already offset by the thread id
+};
+
+template <bool GRAD, int T>
+struct NC { static constexpr int value = GRAD ? T + 1 : 1; };
+
+// (T_i, T_i') of dimension T (1-based), table entry e = i - 2
+template <int T, int E, class CX>
+__device__ __forceinline__ void tab_get(const CX &cx, double &Tv, double &dTv) {
+    if constexpr (T - 1 < CX::TREG) {
+        Tv = cx.tabs[T - 1].t[E];
+        dTv = CX::GRAD ? cx.tabs[T - 1].dt[CX::GRAD ? E : 0] : 0.0;
+    } else {
+        const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + E) * kLeafThreads];
+        Tv = v.x; dTv = v.y;
+    }
+}
+template <int T, class CX>
+__device__ __forceinline__ void tab_x2(const CX &cx, double &x2, double &x2d) {
+    if constexpr (T - 1 < CX::TREG) { x2 = cx.tabs[T - 1].x2; x2d = cx.tabs[T - 1].x2d; }
+    else { const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + kTab) * kLeafThreads]; x2 = v.x; x2d = v.y; }
+}
+
+template <int GK, int T, int R, class CX>
+struct Leaf;
+
+// indices I..ℓ(R) of dimension T
+template <int GK, int T, int R, class CX, int I>
+struct LeafStep {
+    static constexpr bool GRAD = CX::GRAD;
+    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value],
+                                               double &Tc, double &Tq, double &dTc, double &dTq) {
+        if constexpr (I <= ellc<GK>(R)) {
+            constexpr int b = blockof<GK>(I);
+            double Tv, dTv = 0.0;
+            if constexpr (I <= kTab + 1) {
+                tab_get<T, I - 2>(cx, Tv, dTv);
+            } else {
+                double x2, x2d;
+                tab_x2<T>(cx, x2, x2d);
+                if constexpr (I == kTab + 2) {
+                    tab_get<T, kTab - 1>(cx, Tc, dTc);
+                    tab_get<T, kTab - 2>(cx, Tq, dTq);
+                }
+                Tv = fma(x2, Tc, -Tq);
+                if (GRAD) { dTv = fma(x2, dTc, fma(x2d, Tc, -dTq)); dTq = dTc; dTc = dTv; }
+                Tq = Tc; Tc = Tv;
+            }
+            if constexpr (R - b == 0) {
+                // no budget left below: the child is the single coefficient θ (all lower indices are 1,
+                // every lower partial is structurally zero)
+                const double c0 = *th;
+                th += 1;
+                if (GRAD) a[GRAD ? T : 0] = fma(dTv, c0, a[GRAD ? T : 0]);
+                a[0] = fma(Tv, c0, a[0]);
+            } else {
+                double c[NC<GRAD, T - 1>::value];
+                Leaf<GK, T - 1, R - b, CX>::run(cx, th, c);
+                if (GRAD) {
+                    a[GRAD ? T : 0] = fma(dTv, c[0], a[GRAD ? T : 0]);
+#pragma unroll
+                    for (int m = 1; m < T; m++) a[GRAD ? m : 0] = fma(Tv, c[GRAD ? m : 0], a[GRAD ? m : 0]);
+                }
+                a[0] = fma(Tv, c[0], a[0]);
+            }
+            LeafStep<GK, T, R, CX, I + 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
+        }
+    }
+};
+
+template <int GK, int R, class CX>
+struct Leaf<GK, 0, R, CX> {
+    static __device__ __forceinline__ void run(const CX &, const double *&th, double (&a)[1]) {
+        a[0] = *th;
+        th += 1;
+    }
+};
+
+template <int GK, int T, int R, class CX>
+struct Leaf {
+    static constexpr bool GRAD = CX::GRAD;
+    // a[0] = Σ θ·Π T, a[m] = ∂/∂y_m (m = 1..T) over {(i_1..i_T): Σ b_j <= R}; consumes θ in traversal order
+    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value]) {
+        if constexpr (R == 0) {
+            a[0] = *th;
+            th += 1;
+            if (GRAD) {
+#pragma unroll
+                for (int m = 1; m <= T; m++) a[GRAD ? m : 0] = 0.0;
+            }
+        } else {
+            if constexpr (CX::FENCE > 0 && T == CX::FENCE) __syncwarp();
+            {   // index 1: T_0 = 1, derivative 0
+                double c[NC<GRAD, T - 1>::value];
+                Leaf<GK, T - 1, R, CX>::run(cx, th, c);
+                a[0] = c[0];
+                if (GRAD) {
+#pragma unroll
+                    for (int m = 1; m < T; m++) a[GRAD ? m : 0] = c[GRAD ? m : 0];
+                    a[GRAD ? T : 0] = 0.0;
+                }
+            }
+            double Tc = 0, Tq = 0, dTc = 0, dTq = 0;
+            LeafStep<GK, T, R, CX, 2>::run(cx, th, a, Tc, Tq, dTc, dTq);
+        }
+    }
+};
+
+// ---- kernel
+struct LeafParams {
+    const double *x;
+    double *out;
+    const double *theta;
+    const uint32_t *units;        // r | carry << 8
+    int64_t n, K, n_units;
+    int D, nup;
+    sk_transform tr[SK_MAX_DIM];
+};
+
+enum { F_X0 = 0, F_X1, F_X2, F_X2D, F_T, F_TP, F_DT, F_DTP, F_ACC };   // upper-level fields, then ACC[0..D]
+
+// shared memory layout (bytes), shared by host and device
+struct LeafSmem {
+    size_t stab, up, units, theta, total;
+    __host__ __device__ LeafSmem(int LL, int treg, int D, int nup, int64_t n_units, int64_t K) {
+        const int sdims = LL > treg ? LL - treg : 0;
+        stab = 0;
+        up = stab + (size_t)sdims * (kTab + 1) * kLeafThreads * 16;
+        units = up + (size_t)nup * (F_ACC + D + 1) * kLeafThreads * 8;
+        theta = units + (size_t)((n_units + 3) & ~(int64_t)3) * 4;
+        total = theta + (size_t)K * 8;
+    }
+};
+
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE>
+__global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int D = q.D, NUP = q.nup;
+    const int NF = F_ACC + D + 1;
+    const LeafSmem lay(LL, TREG, D, NUP, q.n_units, q.K);
+    double2 *stab = reinterpret_cast<double2 *>(smem_raw + lay.stab) + tid;
+    double *up = reinterpret_cast<double *>(smem_raw + lay.up);           // [NUP][NF][threads]
+    uint32_t *s_units = reinterpret_cast<uint32_t *>(smem_raw + lay.units);
+    double *s_theta = reinterpret_cast<double *>(smem_raw + lay.theta);
+    for (int64_t i = tid; i < q.n_units; i += kLeafThreads) s_units[i] = q.units[i];
+    for (int64_t i = tid; i < q.K; i += kLeafThreads) s_theta[i] = q.theta[i];
+    __syncthreads();
+#define UP(u, f) up[((size_t)(u) * NF + (f)) * kLeafThreads + tid]
+    constexpr int NCL = NC<GRAD, LL>::value;
+    const int E = GRAD ? D + 1 : 1;
+
+    for (int64_t p = (int64_t)blockIdx.x * kLeafThreads + tid; p < q.n; p += (int64_t)gridDim.x * kLeafThreads) {
+        const double *xp = q.x + p * D;
+        using CX = LeafCtx<GRAD, TREG, FENCE>;
+        CX cx;
+        cx.stab = stab;
+#pragma unroll
+        for (int j = 0; j < LL; j++) {
+            double xj[GRAD ? 2 : 1];
+            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[j], xp[j], xj);
+            const double x0 = xj[0], x1 = GRAD ? xj[GRAD ? 1 : 0] : 0.0;
+            double t[kTab], dt[kTab];
+            const double x2 = 2.0 * x0, x2d = 2.0 * x1;
+            t[0] = x0; dt[0] = x1;
+            t[1] = fma(x2, x0, -1.0); dt[1] = x2 * x2d;
+#pragma unroll
+            for (int i = 2; i < kTab; i++) {
+                t[i] = fma(x2, t[i - 1], -t[i - 2]);
+                dt[i] = GRAD ? fma(x2, dt[i - 1], fma(x2d, t[i - 1], -dt[i - 2])) : 0.0;
+            }
+            if (j < TREG) {
+                DimTab<GRAD> &tb = cx.tabs[j < TREG ? j : 0];
+                tb.x2 = x2; tb.x2d = x2d;
+#pragma unroll
+                for (int i = 0; i < kTab; i++) { tb.t[i] = t[i]; if (GRAD) tb.dt[GRAD ? i : 0] = dt[i]; }
+            } else {
+                double2 *sd = stab + (size_t)(j - TREG) * (kTab + 1) * kLeafThreads;
+#pragma unroll
+                for (int i = 0; i < kTab; i++) sd[i * kLeafThreads] = make_double2(t[i], dt[i]);
+                sd[kTab * kLeafThreads] = make_double2(x2, x2d);
+            }
+        }
+        for (int u = 0; u < NUP; u++) {
+            double xj[GRAD ? 2 : 1];
+            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[LL + u], xp[LL + u], xj);
+            UP(u, F_X0) = xj[0]; UP(u, F_X2) = 2.0 * xj[0];
+            if (GRAD) { UP(u, F_X1) = xj[GRAD ? 1 : 0]; UP(u, F_X2D) = 2.0 * xj[GRAD ? 1 : 0]; }
+        }
+        uint32_t first = 0xFFFFFFFFu;                       // bit u: upper level u sits at index 1
+        const double *th = s_theta;
+        double a[NCL];
+        for (int64_t un = 0; un < q.n_units; un++) {
+            const uint32_t w = s_units[un];
+            const int r = (int)(w & 0xFF), c = (int)(w >> 8);
+            switch (r) {
+            case 0: Leaf<GK, LL, 0, CX>::run(cx, th, a); break;
+            case 1: if constexpr (RMAX >= 1) Leaf<GK, LL, RMAX >= 1 ? 1 : 0, CX>::run(cx, th, a); break;
+            case 2: if constexpr (RMAX >= 2) Leaf<GK, LL, RMAX >= 2 ? 2 : 0, CX>::run(cx, th, a); break;
+            case 3: if constexpr (RMAX >= 3) Leaf<GK, LL, RMAX >= 3 ? 3 : 0, CX>::run(cx, th, a); break;
+            case 4: if constexpr (RMAX >= 4) Leaf<GK, LL, RMAX >= 4 ? 4 : 0, CX>::run(cx, th, a); break;
+            case 5: if constexpr (RMAX >= 5) Leaf<GK, LL, RMAX >= 5 ? 5 : 0, CX>::run(cx, th, a); break;
+            default: break;
+            }
+            if (NUP > 0) {
+                // fold the leaf into upper level 0 (dimension LL+1)
+                if (first & 1u) {
+#pragma unroll
+                    for (int m = 0; m < NCL; m++) UP(0, F_ACC + m) = a[m];
+                    if (GRAD) UP(0, F_ACC + LL + 1) = 0.0;
+                } else {
+                    const double Tv = UP(0, F_T);
+#pragma unroll
+                    for (int m = 0; m < NCL; m++) UP(0, F_ACC + m) = fma(Tv, a[m], UP(0, F_ACC + m));
+                    if (GRAD) UP(0, F_ACC + LL + 1) = fma(UP(0, F_DT), a[0], UP(0, F_ACC + LL + 1));
+                }
+                // levels 0..c-1 wrap (fold upwards), level c advances
+                for (int u = 0; u < NUP; u++) {
+                    if (u < c) {
+                        if (u + 1 < NUP) {
+                            const int nc = GRAD ? LL + u + 2 : 1;              // components of level u
+                            if (first & (2u << u)) {
+                                for (int m = 0; m < nc; m++) UP(u + 1, F_ACC + m) = UP(u, F_ACC + m);
+                                if (GRAD) UP(u + 1, F_ACC + nc) = 0.0;
+                            } else {
+                                const double Tv = UP(u + 1, F_T);
+                                for (int m = 0; m < nc; m++) UP(u + 1, F_ACC + m) = fma(Tv, UP(u, F_ACC + m), UP(u + 1, F_ACC + m));
+                                if (GRAD) UP(u + 1, F_ACC + nc) = fma(UP(u + 1, F_DT), UP(u, F_ACC), UP(u + 1, F_ACC + nc));
+                            }
+                        }
+                        first |= 1u << u;
+                    } else {
+                        if (first & (1u << u)) {                                 // index 1 -> 2
+                            UP(u, F_TP) = 1.0; UP(u, F_T) = UP(u, F_X0);
+                            if (GRAD) { UP(u, F_DTP) = 0.0; UP(u, F_DT) = UP(u, F_X1); }
+                            first &= ~(1u << u);
+                        } else {
+                            const double X2 = UP(u, F_X2), Tc = UP(u, F_T), Tq = UP(u, F_TP);
+                            UP(u, F_T) = fma(X2, Tc, -Tq); UP(u, F_TP) = Tc;
+                            if (GRAD) {
+                                const double dTc = UP(u, F_DT);
+                                UP(u, F_DT) = fma(X2, dTc, fma(UP(u, F_X2D), Tc, -UP(u, F_DTP)));
+                                UP(u, F_DTP) = dTc;
+                            }
+                        }
+                        break;
+                    }
+                }
+            }
+        }
+        double *o = q.out + p * E;
+        if (NUP > 0) {
+            for (int m = 0; m < E; m++) o[m] = UP(NUP - 1, F_ACC + m);
+        } else {
+#pragma unroll
+            for (int m = 0; m < NCL; m++) o[m] = a[m];
+        }
+    }
+#undef UP
+}
+
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE>
+cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
+    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE>;
+    const LeafSmem lay(LL, TREG, q.D, q.nup, q.n_units, q.K);
+    const size_t smem = lay.total;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1, dev = 0, sms = 148;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLeafThreads, smem);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (q.n + kLeafThreads - 1) / kLeafThreads;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(per_sm, 1));
+    kern<<<grid, kLeafThreads, smem, stream>>>(q);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// leaf depth / budget combinations that are built (code size and compile time bound the budget)
+constexpr int kLeafMaxLL = 6;
+__host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
+    if (gk == SK_GRID_INTERIOR) return LL <= 2 ? 4 : LL <= 4 ? 3 : 2;
+    return LL <= 4 ? 5 : 4;
+}
+constexpr int leaf_treg_c(int LL) { return LL < SK_TREG ? LL : SK_TREG; }
+constexpr int leaf_minb_c(int LL, bool grad) { return (grad && LL >= 3) ? 2 : 3; }
+constexpr int leaf_fence_c(int) { return 0; }   // __syncwarp fences make ptxas duplicate code: off
+
+// one dispatcher per (family, GRAD), each in its own translation unit (sk_leaf_g*.cu)
+template <int GK, bool GRAD>
+cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
+#ifdef SK_LEAF_VARIANTS
+    if constexpr (GK == SK_GRID_INTERIOR2 && GRAD) {
+        const char *e = getenv("SK_LEAF_VARIANT");
+        const int v = e ? atoi(e) : 0;
+        if (LL == 6 && v > 0) {
+            switch (v) {
+            case 1: return launch_leaf<GK, 6, 4, GRAD, 3, 2, 0>(q, stream);
+            case 2: return launch_leaf<GK, 6, 4, GRAD, 2, 3, 0>(q, stream);
+            case 3: return launch_leaf<GK, 6, 4, GRAD, 2, 2, 0>(q, stream);
+            case 4: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0>(q, stream);
+            case 5: return launch_leaf<GK, 6, 4, GRAD, 1, 3, 0>(q, stream);
+            case 6: return launch_leaf<GK, 6, 4, GRAD, 2, 4, 0>(q, stream);
+            case 7: return launch_leaf<GK, 6, 4, GRAD, 0, 4, 0>(q, stream);
+            }
+        }
+    }
+#endif
+    switch (LL) {
+    case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1), leaf_minb_c(1, GRAD), leaf_fence_c(1)>(q, stream);
+    case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2), leaf_minb_c(2, GRAD), leaf_fence_c(2)>(q, stream);
+    case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3), leaf_minb_c(3, GRAD), leaf_fence_c(3)>(q, stream);
+    case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4), leaf_minb_c(4, GRAD), leaf_fence_c(4)>(q, stream);
+    case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5), leaf_minb_c(5, GRAD), leaf_fence_c(5)>(q, stream);
+    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6), leaf_minb_c(6, GRAD), leaf_fence_c(6)>(q, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace skk
