@@ -39,7 +39,7 @@ bool smolyak_leaf_supported(const sk_plan &plan) {
     int64_t n_units = 1;
     if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
     const LeafSmem lay(LL, leaf_treg_c(LL), d, nup, n_units, plan.K);
-    return lay.total <= 100 * 1024;                              // θ must fit in shared memory next to the rest
+    return lay.total <= 200 * 1024;                              // θ must fit in shared memory next to the rest
 }
 
 // units: distinct tails (i_{LL+1}..i_d) in traversal order; word = r | carry << 8

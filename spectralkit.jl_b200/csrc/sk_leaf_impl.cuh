@@ -44,10 +44,19 @@ __host__ __device__ constexpr int blockof(int i) {
     return b;
 }
 
+// number of index tuples over T dimensions with block budget R
+template <int GK>
+__host__ __device__ constexpr long nterms(int T, int R) {
+    if (T == 0) return 1;
+    long s = 0;
+    for (int i = 1; i <= ellc<GK>(R); i++) s += nterms<GK>(T - 1, R - blockof<GK>(i));
+    return s;
+}
+
 constexpr int kTab = 6;              // table entries: indices 2..7 (degrees 1..6)
-constexpr int kLeafThreads = 128;
+constexpr int kLeafThreads = 256;    // one CTA of 8 warps per SM at 255 registers
 #ifndef SK_TREG
-#define SK_TREG 3                    // dimensions whose table lives in registers
+#define SK_TREG 4                    // dimensions whose table lives in registers
 #endif
 
 template <bool GRAD>
@@ -58,12 +67,14 @@ struct DimTab {
 };
 
 // per-thread evaluation context; the type carries the compile-time configuration
-template <bool GRAD_, int TREG_, int FENCE_>
+template <bool GRAD_, int TREG_, int FENCE_, int LOOPD_>
 struct LeafCtx {
+    static constexpr int LOOPD = LOOPD_;    // dimensions >= LOOPD run one runtime loop per block (must be > TREG)
     static constexpr bool GRAD = GRAD_;
     static constexpr int TREG = TREG_;      // dimensions with register tables
-    static constexpr int FENCE = FENCE_;    // sub-leaves of this many dimensions are separated by a scheduling
-                                            // fence (keeps ptxas from interleaving too many subtrees); 0 = none
+    static constexpr int SYNCT = FENCE_;    // > 0: the CTA re-converges (bar.sync) at the entry of every minimal
+                                            // sub-leaf with at least SYNCT terms, so its warps walk the long
+                                            // straight-line code together and share instruction-cache lines
     DimTab<GRAD_> tabs[TREG_ > 0 ? TREG_ : 1];
     const double2 *stab;                    // shared tables of dims >= TREG, already offset by the thread id
 };
@@ -135,6 +146,58 @@ struct LeafStep {
     }
 };
 
+// Dimensions whose table is in shared memory (T > TREG): one RUNTIME loop per block.  All indices of
+// a block have the same child structure Leaf<T-1, R-b>, so the child code exists once per block and
+// is re-executed from the instruction cache; the table entry is a dynamically indexed LDS.128.
+template <int GK, int T, int R, class CX, int B>
+struct LeafBlocks {
+    static constexpr bool GRAD = CX::GRAD;
+    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value],
+                                               double &Tc, double &Tq, double &dTc, double &dTq) {
+        if constexpr (B <= R) {
+            constexpr int lo = ellc<GK>(B - 1) + 1, hi = ellc<GK>(B);
+            const double2 *tb = cx.stab + (size_t)(T - 1 - CX::TREG) * (kTab + 1) * kLeafThreads;
+            double x2 = 0, x2d = 0;
+            if constexpr (hi > kTab + 1) {
+                const double2 v = tb[kTab * kLeafThreads];
+                x2 = v.x; x2d = v.y;
+                if constexpr (lo <= kTab + 2) {          // the recurrence starts inside (or right at) this block
+                    const double2 e1 = tb[(kTab - 1) * kLeafThreads], e0 = tb[(kTab - 2) * kLeafThreads];
+                    Tc = e1.x; dTc = e1.y; Tq = e0.x; dTq = e0.y;
+                }
+            }
+#pragma unroll 1
+            for (int i = lo; i <= hi; i++) {
+                double Tv, dTv;
+                if (hi <= kTab + 1 || i <= kTab + 1) {
+                    const double2 v = tb[(i - 2) * kLeafThreads];
+                    Tv = v.x; dTv = v.y;
+                } else {
+                    Tv = fma(x2, Tc, -Tq);
+                    dTv = GRAD ? fma(x2, dTc, fma(x2d, Tc, -dTq)) : 0.0;
+                    dTq = dTc; dTc = dTv; Tq = Tc; Tc = Tv;
+                }
+                if constexpr (R - B == 0) {
+                    const double c0 = *th;
+                    th += 1;
+                    if (GRAD) a[GRAD ? T : 0] = fma(dTv, c0, a[GRAD ? T : 0]);
+                    a[0] = fma(Tv, c0, a[0]);
+                } else {
+                    double c[NC<GRAD, T - 1>::value];
+                    Leaf<GK, T - 1, R - B, CX>::run(cx, th, c);
+                    if (GRAD) {
+                        a[GRAD ? T : 0] = fma(dTv, c[0], a[GRAD ? T : 0]);
+#pragma unroll
+                        for (int m = 1; m < T; m++) a[GRAD ? m : 0] = fma(Tv, c[GRAD ? m : 0], a[GRAD ? m : 0]);
+                    }
+                    a[0] = fma(Tv, c[0], a[0]);
+                }
+            }
+            LeafBlocks<GK, T, R, CX, B + 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
+        }
+    }
+};
+
 template <int GK, int R, class CX>
 struct Leaf<GK, 0, R, CX> {
     static __device__ __forceinline__ void run(const CX &, const double *&th, double (&a)[1]) {
@@ -156,7 +219,7 @@ struct Leaf {
                 for (int m = 1; m <= T; m++) a[GRAD ? m : 0] = 0.0;
             }
         } else {
-            if constexpr (CX::FENCE > 0 && T == CX::FENCE) __syncwarp();
+            if constexpr (CX::SYNCT > 0 && nterms<GK>(T, R) >= CX::SYNCT && nterms<GK>(T - 1, R) < CX::SYNCT) __syncthreads();
             {   // index 1: T_0 = 1, derivative 0
                 double c[NC<GRAD, T - 1>::value];
                 Leaf<GK, T - 1, R, CX>::run(cx, th, c);
@@ -168,7 +231,8 @@ struct Leaf {
                 }
             }
             double Tc = 0, Tq = 0, dTc = 0, dTq = 0;
-            LeafStep<GK, T, R, CX, 2>::run(cx, th, a, Tc, Tq, dTc, dTq);
+            if constexpr (T < CX::LOOPD) LeafStep<GK, T, R, CX, 2>::run(cx, th, a, Tc, Tq, dTc, dTq);
+            else LeafBlocks<GK, T, R, CX, 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
         }
     }
 };
@@ -199,7 +263,7 @@ struct LeafSmem {
     }
 };
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD>
 __global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -217,9 +281,13 @@ __global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const 
     constexpr int NCL = NC<GRAD, LL>::value;
     const int E = GRAD ? D + 1 : 1;
 
-    for (int64_t p = (int64_t)blockIdx.x * kLeafThreads + tid; p < q.n; p += (int64_t)gridDim.x * kLeafThreads) {
+    // block-uniform tile loop (the leaf code contains CTA barriers): threads past the end evaluate the
+    // last point again and skip the store
+    for (int64_t p0 = (int64_t)blockIdx.x * kLeafThreads; p0 < q.n; p0 += (int64_t)gridDim.x * kLeafThreads) {
+        const bool live = p0 + tid < q.n;
+        const int64_t p = live ? p0 + tid : q.n - 1;
         const double *xp = q.x + p * D;
-        using CX = LeafCtx<GRAD, TREG, FENCE>;
+        using CX = LeafCtx<GRAD, TREG, FENCE, LOOPD>;
         CX cx;
         cx.stab = stab;
 #pragma unroll
@@ -316,19 +384,21 @@ __global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const 
             }
         }
         double *o = q.out + p * E;
-        if (NUP > 0) {
-            for (int m = 0; m < E; m++) o[m] = UP(NUP - 1, F_ACC + m);
-        } else {
+        if (live) {
+            if (NUP > 0) {
+                for (int m = 0; m < E; m++) o[m] = UP(NUP - 1, F_ACC + m);
+            } else {
 #pragma unroll
-            for (int m = 0; m < NCL; m++) o[m] = a[m];
+                for (int m = 0; m < NCL; m++) o[m] = a[m];
+            }
         }
     }
 #undef UP
 }
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
-    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE>;
+    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD>;
     const LeafSmem lay(LL, TREG, q.D, q.nup, q.n_units, q.K);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -351,37 +421,38 @@ __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
     if (gk == SK_GRID_INTERIOR) return LL <= 2 ? 4 : LL <= 4 ? 3 : 2;
     return LL <= 4 ? 5 : 4;
 }
-constexpr int leaf_treg_c(int LL) { return LL < SK_TREG ? LL : SK_TREG; }
-constexpr int leaf_minb_c(int LL, bool grad) { return (grad && LL >= 3) ? 2 : 3; }
-constexpr int leaf_fence_c(int) { return 0; }   // __syncwarp fences make ptxas duplicate code: off
+constexpr int leaf_treg_c(int LL) { return LL < SK_TREG ? LL : SK_TREG; }   // SK_TREG = 4
+constexpr int leaf_minb_c(int LL, bool grad) { return (grad && LL >= 3) ? 1 : 2; }
+constexpr int leaf_sync_c(int) { return 0; }       // CTA re-convergence granularity (terms); measured: no gain
+constexpr int leaf_loopd_c(int LL, bool grad) { return grad ? 5 : 99; }   // first dimension walked by per-block runtime loops
 
 // one dispatcher per (family, GRAD), each in its own translation unit (sk_leaf_g*.cu)
 template <int GK, bool GRAD>
 cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
 #ifdef SK_LEAF_VARIANTS
-    if constexpr (GK == SK_GRID_INTERIOR2 && GRAD) {
+    if constexpr (GK == SK_GRID_INTERIOR2) {
         const char *e = getenv("SK_LEAF_VARIANT");
         const int v = e ? atoi(e) : 0;
         if (LL == 6 && v > 0) {
             switch (v) {
-            case 1: return launch_leaf<GK, 6, 4, GRAD, 3, 2, 0>(q, stream);
-            case 2: return launch_leaf<GK, 6, 4, GRAD, 2, 3, 0>(q, stream);
-            case 3: return launch_leaf<GK, 6, 4, GRAD, 2, 2, 0>(q, stream);
-            case 4: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0>(q, stream);
-            case 5: return launch_leaf<GK, 6, 4, GRAD, 1, 3, 0>(q, stream);
-            case 6: return launch_leaf<GK, 6, 4, GRAD, 2, 4, 0>(q, stream);
-            case 7: return launch_leaf<GK, 6, 4, GRAD, 0, 4, 0>(q, stream);
+            case 1: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 5>(q, stream);
+            case 2: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 6>(q, stream);
+            case 3: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 5>(q, stream);
+            case 4: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 99>(q, stream);
+            case 5: return launch_leaf<GK, 6, 4, GRAD, 5, 1, 0, 6>(q, stream);
+            case 6: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 6>(q, stream);
+            case 7: return launch_leaf<GK, 6, 4, GRAD, 5, 1, 0, 99>(q, stream);
             }
         }
     }
 #endif
     switch (LL) {
-    case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1), leaf_minb_c(1, GRAD), leaf_fence_c(1)>(q, stream);
-    case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2), leaf_minb_c(2, GRAD), leaf_fence_c(2)>(q, stream);
-    case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3), leaf_minb_c(3, GRAD), leaf_fence_c(3)>(q, stream);
-    case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4), leaf_minb_c(4, GRAD), leaf_fence_c(4)>(q, stream);
-    case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5), leaf_minb_c(5, GRAD), leaf_fence_c(5)>(q, stream);
-    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6), leaf_minb_c(6, GRAD), leaf_fence_c(6)>(q, stream);
+    case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1), leaf_minb_c(1, GRAD), leaf_sync_c(1), leaf_loopd_c(1, GRAD)>(q, stream);
+    case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2), leaf_minb_c(2, GRAD), leaf_sync_c(2), leaf_loopd_c(2, GRAD)>(q, stream);
+    case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3), leaf_minb_c(3, GRAD), leaf_sync_c(3), leaf_loopd_c(3, GRAD)>(q, stream);
+    case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD)>(q, stream);
+    case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD)>(q, stream);
+    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
 }
