@@ -38,7 +38,8 @@ bool smolyak_leaf_supported(const sk_plan &plan) {
     std::vector<uint32_t> units;
     int64_t n_units = 1;
     if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
-    const LeafSmem lay(LL, leaf_treg_c(LL), d, nup, n_units, plan.K);
+    const bool g = plan.fast_mode == 1;
+    const LeafSmem lay(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, plan.K);
     return lay.total <= 200 * 1024;                              // θ must fit in shared memory next to the rest
 }
 

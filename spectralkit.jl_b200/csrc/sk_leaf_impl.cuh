@@ -54,10 +54,6 @@ __host__ __device__ constexpr long nterms(int T, int R) {
 }
 
 constexpr int kTab = 6;              // table entries: indices 2..7 (degrees 1..6)
-constexpr int kLeafThreads = 256;    // one CTA of 8 warps per SM at 255 registers
-#ifndef SK_TREG
-#define SK_TREG 4                    // dimensions whose table lives in registers
-#endif
 
 template <bool GRAD>
 struct DimTab {
@@ -67,8 +63,9 @@ struct DimTab {
 };
 
 // per-thread evaluation context; the type carries the compile-time configuration
-template <bool GRAD_, int TREG_, int FENCE_, int LOOPD_>
+template <bool GRAD_, int TREG_, int FENCE_, int LOOPD_, int NT_>
 struct LeafCtx {
+    static constexpr int NT = NT_;          // threads per CTA (stride of the shared per-thread arrays)
     static constexpr int LOOPD = LOOPD_;    // dimensions >= LOOPD run one runtime loop per block (must be > TREG)
     static constexpr bool GRAD = GRAD_;
     static constexpr int TREG = TREG_;      // dimensions with register tables
@@ -89,14 +86,14 @@ __device__ __forceinline__ void tab_get(const CX &cx, double &Tv, double &dTv) {
         Tv = cx.tabs[T - 1].t[E];
         dTv = CX::GRAD ? cx.tabs[T - 1].dt[CX::GRAD ? E : 0] : 0.0;
     } else {
-        const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + E) * kLeafThreads];
+        const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + E) * CX::NT];
         Tv = v.x; dTv = v.y;
     }
 }
 template <int T, class CX>
 __device__ __forceinline__ void tab_x2(const CX &cx, double &x2, double &x2d) {
     if constexpr (T - 1 < CX::TREG) { x2 = cx.tabs[T - 1].x2; x2d = cx.tabs[T - 1].x2d; }
-    else { const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + kTab) * kLeafThreads]; x2 = v.x; x2d = v.y; }
+    else { const double2 v = cx.stab[((T - 1 - CX::TREG) * (kTab + 1) + kTab) * CX::NT]; x2 = v.x; x2d = v.y; }
 }
 
 template <int GK, int T, int R, class CX>
@@ -156,13 +153,13 @@ struct LeafBlocks {
                                                double &Tc, double &Tq, double &dTc, double &dTq) {
         if constexpr (B <= R) {
             constexpr int lo = ellc<GK>(B - 1) + 1, hi = ellc<GK>(B);
-            const double2 *tb = cx.stab + (size_t)(T - 1 - CX::TREG) * (kTab + 1) * kLeafThreads;
+            const double2 *tb = cx.stab + (size_t)(T - 1 - CX::TREG) * (kTab + 1) * CX::NT;
             double x2 = 0, x2d = 0;
             if constexpr (hi > kTab + 1) {
-                const double2 v = tb[kTab * kLeafThreads];
+                const double2 v = tb[kTab * CX::NT];
                 x2 = v.x; x2d = v.y;
                 if constexpr (lo <= kTab + 2) {          // the recurrence starts inside (or right at) this block
-                    const double2 e1 = tb[(kTab - 1) * kLeafThreads], e0 = tb[(kTab - 2) * kLeafThreads];
+                    const double2 e1 = tb[(kTab - 1) * CX::NT], e0 = tb[(kTab - 2) * CX::NT];
                     Tc = e1.x; dTc = e1.y; Tq = e0.x; dTq = e0.y;
                 }
             }
@@ -170,7 +167,7 @@ struct LeafBlocks {
             for (int i = lo; i <= hi; i++) {
                 double Tv, dTv;
                 if (hi <= kTab + 1 || i <= kTab + 1) {
-                    const double2 v = tb[(i - 2) * kLeafThreads];
+                    const double2 v = tb[(i - 2) * CX::NT];
                     Tv = v.x; dTv = v.y;
                 } else {
                     Tv = fma(x2, Tc, -Tq);
@@ -253,41 +250,41 @@ enum { F_X0 = 0, F_X1, F_X2, F_X2D, F_T, F_TP, F_DT, F_DTP, F_ACC };   // upper-
 // shared memory layout (bytes), shared by host and device
 struct LeafSmem {
     size_t stab, up, units, theta, total;
-    __host__ __device__ LeafSmem(int LL, int treg, int D, int nup, int64_t n_units, int64_t K) {
+    __host__ __device__ LeafSmem(int NT, int LL, int treg, int D, int nup, int64_t n_units, int64_t K) {
         const int sdims = LL > treg ? LL - treg : 0;
         stab = 0;
-        up = stab + (size_t)sdims * (kTab + 1) * kLeafThreads * 16;
-        units = up + (size_t)nup * (F_ACC + D + 1) * kLeafThreads * 8;
+        up = stab + (size_t)sdims * (kTab + 1) * NT * 16;
+        units = up + (size_t)nup * (F_ACC + D + 1) * NT * 8;
         theta = units + (size_t)((n_units + 3) & ~(int64_t)3) * 4;
         total = theta + (size_t)K * 8;
     }
 };
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD>
-__global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
+__global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int D = q.D, NUP = q.nup;
     const int NF = F_ACC + D + 1;
-    const LeafSmem lay(LL, TREG, D, NUP, q.n_units, q.K);
+    const LeafSmem lay(NT, LL, TREG, D, NUP, q.n_units, q.K);
     double2 *stab = reinterpret_cast<double2 *>(smem_raw + lay.stab) + tid;
     double *up = reinterpret_cast<double *>(smem_raw + lay.up);           // [NUP][NF][threads]
     uint32_t *s_units = reinterpret_cast<uint32_t *>(smem_raw + lay.units);
     double *s_theta = reinterpret_cast<double *>(smem_raw + lay.theta);
-    for (int64_t i = tid; i < q.n_units; i += kLeafThreads) s_units[i] = q.units[i];
-    for (int64_t i = tid; i < q.K; i += kLeafThreads) s_theta[i] = q.theta[i];
+    for (int64_t i = tid; i < q.n_units; i += NT) s_units[i] = q.units[i];
+    for (int64_t i = tid; i < q.K; i += NT) s_theta[i] = q.theta[i];
     __syncthreads();
-#define UP(u, f) up[((size_t)(u) * NF + (f)) * kLeafThreads + tid]
+#define UP(u, f) up[((size_t)(u) * NF + (f)) * NT + tid]
     constexpr int NCL = NC<GRAD, LL>::value;
     const int E = GRAD ? D + 1 : 1;
 
     // block-uniform tile loop (the leaf code contains CTA barriers): threads past the end evaluate the
     // last point again and skip the store
-    for (int64_t p0 = (int64_t)blockIdx.x * kLeafThreads; p0 < q.n; p0 += (int64_t)gridDim.x * kLeafThreads) {
+    for (int64_t p0 = (int64_t)blockIdx.x * NT; p0 < q.n; p0 += (int64_t)gridDim.x * NT) {
         const bool live = p0 + tid < q.n;
         const int64_t p = live ? p0 + tid : q.n - 1;
         const double *xp = q.x + p * D;
-        using CX = LeafCtx<GRAD, TREG, FENCE, LOOPD>;
+        using CX = LeafCtx<GRAD, TREG, FENCE, LOOPD, NT>;
         CX cx;
         cx.stab = stab;
 #pragma unroll
@@ -310,10 +307,10 @@ __global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const 
 #pragma unroll
                 for (int i = 0; i < kTab; i++) { tb.t[i] = t[i]; if (GRAD) tb.dt[GRAD ? i : 0] = dt[i]; }
             } else {
-                double2 *sd = stab + (size_t)(j - TREG) * (kTab + 1) * kLeafThreads;
+                double2 *sd = stab + (size_t)(j - TREG) * (kTab + 1) * NT;
 #pragma unroll
-                for (int i = 0; i < kTab; i++) sd[i * kLeafThreads] = make_double2(t[i], dt[i]);
-                sd[kTab * kLeafThreads] = make_double2(x2, x2d);
+                for (int i = 0; i < kTab; i++) sd[i * NT] = make_double2(t[i], dt[i]);
+                sd[kTab * NT] = make_double2(x2, x2d);
             }
         }
         for (int u = 0; u < NUP; u++) {
@@ -396,21 +393,21 @@ __global__ void __launch_bounds__(kLeafThreads, MINB) smolyak_leaf_kernel(const 
 #undef UP
 }
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
-    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD>;
-    const LeafSmem lay(LL, TREG, q.D, q.nup, q.n_units, q.K);
+    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT>;
+    const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.K);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1, dev = 0, sms = 148;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLeafThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t tiles = (q.n + kLeafThreads - 1) / kLeafThreads;
+    const int64_t tiles = (q.n + NT - 1) / NT;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(per_sm, 1));
-    kern<<<grid, kLeafThreads, smem, stream>>>(q);
+    kern<<<grid, NT, smem, stream>>>(q);
     count_launch();
     return cudaGetLastError();
 }
@@ -421,10 +418,14 @@ __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
     if (gk == SK_GRID_INTERIOR) return LL <= 2 ? 4 : LL <= 4 ? 3 : 2;
     return LL <= 4 ? 5 : 4;
 }
-constexpr int leaf_treg_c(int LL) { return LL < SK_TREG ? LL : SK_TREG; }   // SK_TREG = 4
-constexpr int leaf_minb_c(int LL, bool grad) { return (grad && LL >= 3) ? 1 : 2; }
+// tuning measured on B200 for the d = 6, B = 4 gradient case (profiles/r1_leaf_variants.md): 12 warps/SM at
+// 168 registers with two register tables and only the top dimension looped is the best trade between
+// latency hiding, spills and instruction-cache reuse
+constexpr int leaf_treg_c(int LL, bool grad) { const int t = grad ? (LL >= 5 ? 2 : 3) : (LL >= 5 ? 3 : 4); return LL < t ? LL : t; }
+constexpr int leaf_minb_c(int LL, bool grad) { return (LL >= 5 || (grad && LL >= 3)) ? 1 : 2; }
+constexpr int leaf_nt_c(int LL, bool grad) { return LL >= 5 ? (grad ? 384 : 512) : 256; }   // threads per CTA
 constexpr int leaf_sync_c(int) { return 0; }       // CTA re-convergence granularity (terms); measured: no gain
-constexpr int leaf_loopd_c(int LL, bool grad) { return grad ? 5 : 99; }   // first dimension walked by per-block runtime loops
+constexpr int leaf_loopd_c(int LL, bool grad) { return grad && LL >= 5 ? LL : 99; }   // first dimension walked by per-block runtime loops
 
 // one dispatcher per (family, GRAD), each in its own translation unit (sk_leaf_g*.cu)
 template <int GK, bool GRAD>
@@ -435,24 +436,25 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
         const int v = e ? atoi(e) : 0;
         if (LL == 6 && v > 0) {
             switch (v) {
-            case 1: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 5>(q, stream);
-            case 2: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 6>(q, stream);
-            case 3: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 5>(q, stream);
-            case 4: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 99>(q, stream);
-            case 5: return launch_leaf<GK, 6, 4, GRAD, 5, 1, 0, 6>(q, stream);
-            case 6: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 6>(q, stream);
-            case 7: return launch_leaf<GK, 6, 4, GRAD, 5, 1, 0, 99>(q, stream);
+            case 1: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0, 99, 256>(q, stream);
+            case 2: return launch_leaf<GK, 6, 4, GRAD, 3, 2, 0, 99, 256>(q, stream);
+            case 3: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0, 6, 256>(q, stream);
+            case 4: return launch_leaf<GK, 6, 4, GRAD, 3, 3, 0, 99, 256>(q, stream);
+            case 5: return launch_leaf<GK, 6, 4, GRAD, 4, 4, 0, 99, 128>(q, stream);
+            case 6: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 99, 512>(q, stream);
+            case 7: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 99, 512>(q, stream);
+            case 8: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 99, 768>(q, stream);
             }
         }
     }
 #endif
     switch (LL) {
-    case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1), leaf_minb_c(1, GRAD), leaf_sync_c(1), leaf_loopd_c(1, GRAD)>(q, stream);
-    case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2), leaf_minb_c(2, GRAD), leaf_sync_c(2), leaf_loopd_c(2, GRAD)>(q, stream);
-    case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3), leaf_minb_c(3, GRAD), leaf_sync_c(3), leaf_loopd_c(3, GRAD)>(q, stream);
-    case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD)>(q, stream);
-    case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD)>(q, stream);
-    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD)>(q, stream);
+    case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1, GRAD), leaf_minb_c(1, GRAD), leaf_sync_c(1), leaf_loopd_c(1, GRAD), leaf_nt_c(1, GRAD)>(q, stream);
+    case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2, GRAD), leaf_minb_c(2, GRAD), leaf_sync_c(2), leaf_loopd_c(2, GRAD), leaf_nt_c(2, GRAD)>(q, stream);
+    case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3, GRAD), leaf_minb_c(3, GRAD), leaf_sync_c(3), leaf_loopd_c(3, GRAD), leaf_nt_c(3, GRAD)>(q, stream);
+    case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4, GRAD), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD), leaf_nt_c(4, GRAD)>(q, stream);
+    case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5, GRAD), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD), leaf_nt_c(5, GRAD)>(q, stream);
+    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
 }
