@@ -106,7 +106,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     cores = orc.max_threads()
-    sample = 20000 * cores
+    sample = 60000 * cores
     rate, cores, dt = cpu_reference_rate(sample, seed=104, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "smolyak_d6_B4_linear_combination_Mpoints_per_s", "value": rate, "unit": "Mpoints/s",
@@ -159,8 +159,7 @@ def run_ours(args):
     theta = torch.empty(K, dtype=torch.float64, device=dev)
     if rank == 0:
         theta.copy_(torch.as_tensor(np.random.default_rng(4).standard_normal(K)))
-    if world > 1:
-        dist.broadcast(theta, 0)
+    sk.broadcast_coefficients(theta, 0)
 
     # synthetic points: per-coordinate u ~ U(-0.99, 0.99) mapped by transform_from (SURVEY.md §8(d) cfg 4)
     gen = torch.Generator(device=dev).manual_seed(104 + rank)
@@ -267,7 +266,7 @@ def run_ours(args):
                        "basis_term_evals_per_s": value * 1e6 * K, "l2_policy": "inputs (4.8 GB/GPU) and outputs (5.6 GB/GPU) far exceed the 126 MB L2",
                        "parallelism": f"points sharded over {world} GPU(s), θ broadcast once"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_sust, "unit": "TFLOP/s", "frac": achieved / dfma_sust,
-                         "traffic": traffic, "kernel": "smolyak_nested_kernel<6,true>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "smolyak_leaf_kernel<InteriorGrid2, LL=6, GRAD> (spectralkit.jl_b200/csrc/sk_leaf_impl.cuh)", "kernel_ms": kernel_ms,
                          "flops_per_point": flops_pt, "flops_per_point_reference_direct": float(info.flops_per_point_direct),
                          "peak_source": "measured live: sk_fp64_peak DFMA sustained (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2 TFLOP/s",
                          "peak_burst": dfma_burst, "hbm_gbs": hbm_gbs,
@@ -280,7 +279,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
             cores = orc.max_threads()
-            sample = 20000 * cores
+            sample = 100000 * cores
             rate, cores, dt = cpu_reference_rate(sample, seed=104)
             line["cpu_baseline"] = {"value": rate, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                                     "sample": f"first-seed {sample} points of the same workload, {dt:.1f} s; C restatement of the reference (Julia not installed)"}

@@ -1,0 +1,179 @@
+# SpectralKitB200.jl — Julia `ccall` shim over libspectralkit_b200.so (include/spectralkit_b200.h).
+#
+# STATUS: written against the C ABI but NEVER EXECUTED — Julia is not installed in the build image
+# or on the GPU box (SURVEY.md §0 fact 2).  The executable harness with the same semantics is the
+# Python mirror (spectralkit.jl_b200/api.py); every call below has a one-to-one counterpart there.
+#
+# What it does: keeps SpectralKit.jl's own types (bases, transformations, 𝑑/∂ requests are built by
+# the reference's constructors, so every DomainError/ArgumentError of a constructor is the
+# reference's own) and adds BATCHED methods that hand whole point collections to the GPU:
+#
+#     using SpectralKit, SpectralKitB200
+#     basis = smolyak_basis(Chebyshev, InteriorGrid2(), SmolyakParameters(4), 6) ∘ ct
+#     θ  = randn(dimension(basis))
+#     xs = [ntuple(_ -> rand(), 6) for _ in 1:10^6]          # Vector{NTuple{6,Float64}}
+#     ys = linear_combination(basis, θ, ∂gradient(6), xs)     # Vector{SVector{7,Float64}}, on the GPU
+#     C  = collocation_matrix_gpu(basis, xs)                  # Matrix{Float64}, on the GPU
+#
+# Memory: Julia's `Vector{NTuple{d,Float64}}`, `Vector{SVector{M,Float64}}`, `d×n Matrix{Float64}`
+# and `Matrix{Float64}` already have the layouts the C ABI takes, so pointers are passed through
+# (GC.@preserve) without copies on the Julia side.
+module SpectralKitB200
+
+using SpectralKit
+using SpectralKit: Chebyshev, SmolyakBasis, SmolyakIndices, TransformedBasis, BoundedLinear,
+    SemiInfRational, InfRational, CoordinateTransformations, InteriorGrid, EndpointGrid, InteriorGrid2,
+    𝑑Derivatives, ∂Derivatives, Partials, _partials_canonical_expansion
+using StaticArrays
+
+export ∂gradient, collocation_matrix_gpu, basis_at_gpu, SKPlan
+
+const libsk = get(ENV, "SPECTRALKIT_B200_LIB", joinpath(@__DIR__, "..", "lib", "libspectralkit_b200.so"))
+
+# ---- C structs (include/spectralkit_b200.h) ----------------------------------------------------
+struct SkBasisDesc
+    kind::Int32; grid_kind::Int32; N::Int32; d::Int32; B::Int32; M::Int32
+end
+struct SkTransform
+    kind::Int32; reserved::Int32; p0::Float64; p1::Float64
+end
+struct SkDerivSpec
+    order::Int32; ncomp::Int32; orders::Ptr{Int32}; allow_rational_d2::Int32
+end
+
+const SK_MEM_HOST, SK_MEM_DEVICE, SK_MODE_FAST, SK_MODE_EXACT = UInt32(0), UInt32(1), UInt32(0), UInt32(2)
+
+# status codes → the reference's exception types (SURVEY.md §8(b) "Errors")
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:sk_last_error, libsk), Cstring, ()))
+    rc == -1 && throw(ArgumentError(msg))
+    rc == -2 && throw(DomainError(msg))
+    rc == -3 && error(msg)                       # "… not implemented yet", MethodError-like cases
+    error("spectralkit_b200: CUDA failure or no device (status $rc): $msg")   # no CPU fallback
+end
+
+grid_code(::InteriorGrid) = Int32(0)
+grid_code(::EndpointGrid) = Int32(1)
+grid_code(::InteriorGrid2) = Int32(2)
+
+desc(b::Chebyshev) = SkBasisDesc(0, grid_code(b.grid_kind), b.N, 1, 0, 0)
+function desc(b::SmolyakBasis{<:SmolyakIndices{N,H,B,M}}) where {N,H,B,M}
+    SkBasisDesc(1, grid_code(b.univariate_parent.grid_kind), 0, N, B, M)
+end
+
+# the reference's stored fields travel unchanged (src/transformations.jl:150-153, 207-210, 281-284)
+sk(t::BoundedLinear) = SkTransform(1, 0, t.m, t.s)
+sk(t::SemiInfRational) = SkTransform(2, 0, t.A, t.L)
+sk(t::InfRational) = SkTransform(3, 0, t.A, t.L)
+
+split(b::TransformedBasis) = (b.parent, b.transformation isa CoordinateTransformations ?
+                              SkTransform[sk(t) for t in Tuple(b.transformation)] : SkTransform[sk(b.transformation)])
+split(b) = (b, nothing)
+
+"`∂(1) ∪ ∂(0,1) ∪ …`: value and all first partials of an `n`-dimensional argument."
+∂gradient(n::Int) = reduce(∪, (∂(ntuple(j -> j == i ? 1 : 0, i)...) for i in 1:n))
+
+# canonical expansion of a ∂ specification as the Int32 table the ABI takes (derivatives.jl:284-300)
+function order_table(::∂Derivatives{Ps}, N::Int) where {Ps}
+    exp = collect(_partials_canonical_expansion(Val(N), fieldtypes(Ps)))
+    Int32[exp[c][j] for j in 1:N, c in eachindex(exp)]          # column c = component c: [ncomp][N] in C order
+end
+
+# ---- plans --------------------------------------------------------------------------------------
+mutable struct SKPlan
+    handle::Ptr{Cvoid}
+    E::Int
+    K::Int
+    function SKPlan(basis; order::Int = 0, spec::Union{Nothing,∂Derivatives} = nothing, device::Int = 0,
+                    allow_rational_d2::Bool = false)
+        parent, trs = split(basis)
+        d = desc(parent)
+        table = spec === nothing ? Int32[] : vec(order_table(spec, Int(d.d)))
+        ncomp = spec === nothing ? 0 : length(table) ÷ d.d
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve table begin
+            ds = SkDerivSpec(order, ncomp, isempty(table) ? C_NULL : pointer(table), allow_rational_d2)
+            check(ccall((:sk_plan_create, libsk), Cint,
+                        (Ref{SkBasisDesc}, Ptr{SkTransform}, Ref{SkDerivSpec}, Cint, Ref{Ptr{Cvoid}}),
+                        d, trs === nothing ? C_NULL : trs, ds, device, h))
+        end
+        E = spec === nothing ? order + 1 : max(ncomp, 1)
+        p = new(h[], E, dimension(basis))
+        finalizer(q -> ccall((:sk_plan_destroy, libsk), Cint, (Ptr{Cvoid},), q.handle), p)
+        p
+    end
+end
+
+const PLANS = Dict{Any,SKPlan}()
+plan_for(basis; kw...) = get!(() -> SKPlan(basis; kw...), PLANS, (basis, kw))
+
+# ---- batched linear_combination (generic_api.jl:114-138) ----------------------------------------
+# univariate: xs::AbstractVector{Float64}; `𝑑^D` requests derivatives (derivatives.jl:66-107)
+function SpectralKit.linear_combination(basis, θ::Vector{Float64}, xs::Vector{Float64};
+                                        D::𝑑Derivatives{Dn} = 𝑑Derivatives{0}(), exact::Bool = false) where {Dn}
+    p = plan_for(basis; order = Dn)
+    out = Matrix{Float64}(undef, Dn + 1, length(xs))          # column i = 𝑑Expansion of point i
+    flags = SK_MEM_HOST | (exact ? SK_MODE_EXACT : SK_MODE_FAST)
+    GC.@preserve θ xs out check(ccall((:sk_linear_combination, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, UInt32, Ptr{Cvoid}),
+        p.handle, θ, length(θ), 1, xs, length(xs), out, flags, C_NULL))
+    Dn == 0 ? vec(out) : [SpectralKit.𝑑Expansion(SVector{Dn + 1}(view(out, :, i))) for i in axes(out, 2)]
+end
+
+# multivariate: xs::Vector{NTuple{N,Float64}} (or Vector{SVector{N}}); `spec` is a ∂ request or nothing
+function SpectralKit.linear_combination(basis, θ::Vector{Float64}, spec::Union{Nothing,∂Derivatives},
+                                        xs::Vector{<:Union{NTuple{N,Float64},SVector{N,Float64}}};
+                                        exact::Bool = false) where {N}
+    p = plan_for(basis; spec = spec)
+    out = Matrix{Float64}(undef, p.E, length(xs))
+    flags = SK_MEM_HOST | (exact ? SK_MODE_EXACT : SK_MODE_FAST)
+    GC.@preserve θ xs out check(ccall((:sk_linear_combination, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, UInt32, Ptr{Cvoid}),
+        p.handle, θ, length(θ), 1, Ptr{Float64}(pointer(xs)), length(xs), out, flags, C_NULL))
+    spec === nothing ? vec(out) :
+        [SpectralKit.∂Expansion(spec, SVector{size(out, 1)}(view(out, :, i))) for i in axes(out, 2)]
+end
+
+# SVector coefficients (test/test_generic_api.jl:95-102): θ::Vector{SVector{M,Float64}}
+function SpectralKit.linear_combination(basis, θ::Vector{SVector{M,Float64}}, xs::Vector{Float64}) where {M}
+    p = plan_for(basis)
+    out = Vector{SVector{M,Float64}}(undef, length(xs))
+    GC.@preserve θ xs out check(ccall((:sk_linear_combination, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, UInt32, Ptr{Cvoid}),
+        p.handle, Ptr{Float64}(pointer(θ)), length(θ), M, xs, length(xs), Ptr{Float64}(pointer(out)), SK_MEM_HOST, C_NULL))
+    out
+end
+
+# ---- collocation_matrix / basis_at (generic_api.jl:217-227): column-major n×K, as the reference ----
+function collocation_matrix_gpu(basis, xs::Vector{Float64} = collect(grid(basis)))
+    p = plan_for(basis)
+    C = Matrix{Float64}(undef, length(xs), p.K)
+    GC.@preserve xs C check(ccall((:sk_basis_at, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, UInt32, Ptr{Cvoid}),
+        p.handle, xs, length(xs), C, length(xs), SK_MEM_HOST, C_NULL))
+    C
+end
+function collocation_matrix_gpu(basis, xs::Vector{<:Union{NTuple{N,Float64},SVector{N,Float64}}}) where {N}
+    p = plan_for(basis)
+    C = Matrix{Float64}(undef, length(xs), p.K)
+    GC.@preserve xs C check(ccall((:sk_basis_at, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, UInt32, Ptr{Cvoid}),
+        p.handle, Ptr{Float64}(pointer(xs)), length(xs), C, length(xs), SK_MEM_HOST, C_NULL))
+    C
+end
+const basis_at_gpu = collocation_matrix_gpu
+
+# ---- metadata that must be bit-exact (SURVEY.md §8(b)) -------------------------------------------
+"collect(grid(basis)) computed by the library (correctly rounded sinpi/cospi); compare with `collect(grid(basis))`."
+function grid_gpu_library(basis)
+    parent, trs = split(basis)
+    d = desc(parent)
+    K = dimension(basis)
+    out = d.kind == 0 ? Vector{Float64}(undef, K) : Matrix{Float64}(undef, Int(d.d), K)
+    GC.@preserve out check(ccall((:sk_grid, libsk), Cint, (Ref{SkBasisDesc}, Ptr{SkTransform}, Ptr{Float64}),
+                                 d, trs === nothing ? C_NULL : trs, out))
+    out
+end
+
+end # module
