@@ -294,6 +294,12 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         CK(cudaMemcpy(p->d_idx, p->set.idx.data(), p->set.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&p->d_runs, prog.size() * sizeof(uint32_t)));
         CK(cudaMemcpy(p->d_runs, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (p->ncomp == 0) {
+            std::vector<uint8_t> adv;
+            skk::smolyak_block_program(*p, adv);
+            CK(cudaMalloc(&p->d_adv, adv.size()));
+            CK(cudaMemcpy(p->d_adv, adv.data(), adv.size(), cudaMemcpyHostToDevice));
+        }
         if (p->fast_kernel == 2) {
             std::vector<uint32_t> units;
             skk::smolyak_leaf_units(*p, units);
@@ -313,6 +319,7 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_idx) cudaFree(plan->d_idx);
         if (plan->d_runs) cudaFree(plan->d_runs);
         if (plan->d_units) cudaFree(plan->d_units);
+        if (plan->d_adv) cudaFree(plan->d_adv);
     }
     delete plan;
     return SK_OK;
@@ -349,6 +356,10 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
     }
     if (!exact && nvec == 1 && plan->fast_kernel == 1) {
         CK(skk::smolyak_nested_lincomb(*plan, d_theta, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    if (!exact && nvec > 1 && skk::smolyak_block_supported(*plan)) {
+        CK(skk::smolyak_block_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
     CK(skk::smolyak_direct_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
@@ -558,7 +569,7 @@ int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double 
 
 // ------------------------------------------------------------------------------ measurement
 int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained) {
-    if (which < 0 || which > 1 || !tflops_burst || !tflops_sustained) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
+    if (which < 0 || which > 2 || !tflops_burst || !tflops_sustained) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
     int ndev = 0;
     int rc = sk_device_count(&ndev);
     if (rc != SK_OK) return rc;

@@ -70,6 +70,7 @@ struct sk_plan {
     int64_t n_runs = 0;
     uint32_t *d_units = nullptr; // [n_units] r | carry << 8             (unrolled-leaf kernel)
     int64_t n_units = 0;
+    uint8_t *d_adv = nullptr;    // [ceil16(K)] advance program (coefficient-block kernel)
     int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves
     double flops_fast = 0, flops_direct = 0;
 };

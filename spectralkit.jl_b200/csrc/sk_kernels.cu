@@ -544,9 +544,43 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// which == 2: even warps run the DFMA chains, odd warps the DMMA tiles — do the two share one pipe?
+__global__ void __launch_bounds__(256) dmix_peak_kernel(int iters, double *sink) {
+    double s = 0;
+    if ((threadIdx.x >> 5) & 1) {
+        double c[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+        double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    } else {
+        double a[16];
+        const double m = 1.0000001, c = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = 1.0 + i * 1e-3 + threadIdx.x * 1e-6;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) s += a[i];
+    }
+    if (s == 123.456) sink[0] = s;
+}
+
 cudaError_t fp64_peak_launch(int which, int iters, double *sink, double *flops, cudaStream_t stream) {
     int blocks = sm_count() * 8, threads = 256;
-    if (which == 0) {
+    if (which == 2) {
+        dmix_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+        *flops = (2.0 * 16 * 32 + 2.0 * 8 * 8 * 4 * 8) * (double)iters * blocks * (threads / 64);
+    } else if (which == 0) {
         dfma_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
         *flops = 2.0 * 16 * (double)iters * blocks * threads;
     } else {

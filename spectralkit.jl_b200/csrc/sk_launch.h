@@ -33,6 +33,13 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, const
                                  double *out, cudaStream_t stream);
 double smolyak_leaf_flops(const sk_plan &plan);
 
+// ---- Smolyak with a K×nvec coefficient block: on-chip collocation tiles × Θ with FP64 DMMA (sk_block.cu)
+bool smolyak_block_supported(const sk_plan &plan);
+void smolyak_block_program(const sk_plan &plan, std::vector<uint8_t> &adv);
+cudaError_t smolyak_block_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
+                                  double *out, cudaStream_t stream);
+double smolyak_block_flops(const sk_plan &plan, int nvec);
+
 // ---- coordinate transformations over n×d points
 cudaError_t transform_to(const sk_transform *tr, int d, int order, const double *y, int64_t n, double *out,
                          cudaStream_t stream);

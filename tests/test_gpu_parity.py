@@ -360,6 +360,62 @@ def test_smolyak_svector_coefficients(orc):
         assert same(got[:, v], sk.linear_combination(basis, theta[:, v].copy(), x, exact=True))
 
 
+# ---- K4: coefficient block (SVector coefficients) through the DMMA kernel, fast mode
+@pytest.mark.parametrize("code,d,B,nvec,n", [
+    (2, 4, 3, 11, 100),      # odd nvec: generic Θ loader, scalar epilogue stores; partial point tile
+    (2, 4, 3, 2, 300),       # smallest block, 8-wide tile
+    (0, 3, 2, 12, 257),      # InteriorGrid, 16-wide tile
+    (1, 5, 3, 24, 129),      # EndpointGrid, 32-wide tile
+    (2, 6, 4, 40, 200),      # 64-wide tile
+    (2, 6, 4, 100, 130),     # 128-wide tile, partial vector tile
+    (2, 3, 5, 256, 70),      # 256-wide tile, high budget in few dimensions
+    (2, 6, 4, 300, 65),      # two vector tiles (256 + 44)
+    (1, 12, 2, 16, 90),      # more than 10 dimensions
+    (2, 1, 4, 8, 50),        # one-dimensional Smolyak basis
+])
+def test_smolyak_block_fast(orc, code, d, B, nvec, n):
+    rng = np.random.default_rng(7000 + 13 * d + nvec)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    K = sk.dimension(basis)
+    theta = rng.standard_normal((K, nvec))
+    x = rand_pm1(rng, (n, d))
+    want = orc.smolyak_lincomb(code, d, B, B, theta, x)
+    scale = orc.smolyak_lincomb(code, d, B, B, theta, x, absmode=True)
+    got = sk.linear_combination(basis, theta, x)
+    assert got.shape == (n, nvec) and within(got, want, scale)
+    # device-resident, and consistent with the bit-exact direct kernel
+    import torch
+    gdev = sk.linear_combination(basis, torch.as_tensor(theta).cuda(), torch.as_tensor(x).cuda())
+    assert same(gdev.cpu().numpy(), got)
+    assert same(sk.linear_combination(basis, theta, x, exact=True), want)
+
+
+def test_smolyak_block_transformed_cfg5_shape(orc):
+    # cfg 5 geometry (d = 10, B = 5, K = 77 505, 256 coefficient vectors) on a handful of points, with
+    # coordinate transformations mixed in; Θ is 159 MB
+    rng = np.random.default_rng(505)
+    d, B, nvec, n = 10, 5, 256, 70
+    kinds = [(1, -1, 1), (1, 0, 4), (2, 1, 2), (3, 0, 4), (1, -1, 2), (2, -3, 3), (1, -2, 2), (3, 1, 1), (1, 0, 1), (2, 0.5, 1)]
+    trs = [mk_tr(orc, *k) for k in kinds]
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    ct = sk.coordinate_transformations(*[t[0] for t in trs])
+    K = sk.dimension(basis)
+    assert K == 77505
+    theta = rng.standard_normal((K, nvec))
+    u = rng.uniform(-0.99, 0.99, (n, d))
+    y = sk.transform_from(basis, ct, u)
+    otr = [t[1] for t in trs]
+    want = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr)
+    scale = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, absmode=True)
+    got = sk.linear_combination(basis @ ct, theta, y)
+    assert within(got, want, scale)
+    # linearity in Θ (size-independent property): columns scaled and summed
+    th2 = np.ascontiguousarray(theta[:, :8] @ rng.standard_normal((8, 8)))
+    g8 = sk.linear_combination(basis @ ct, np.ascontiguousarray(theta[:, :8]), y)
+    w = np.linalg.solve(theta[:8, :8], th2[:8, :8])          # th2 = theta[:, :8] @ w
+    np.testing.assert_allclose(sk.linear_combination(basis @ ct, th2, y), g8 @ w, rtol=1e-9, atol=1e-9 * np.abs(scale[:, :8]).max())
+
+
 def test_golden_fixtures(orc):
     g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
     b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
