@@ -295,10 +295,11 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         CK(cudaMalloc(&p->d_runs, prog.size() * sizeof(uint32_t)));
         CK(cudaMemcpy(p->d_runs, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         if (p->ncomp == 0) {
-            std::vector<uint8_t> adv;
-            skk::smolyak_block_program(*p, adv);
-            CK(cudaMalloc(&p->d_adv, adv.size()));
-            CK(cudaMemcpy(p->d_adv, adv.data(), adv.size(), cudaMemcpyHostToDevice));
+            std::vector<uint32_t> bprog;
+            if (skk::smolyak_block_program(*p, bprog, &p->bprog_F, &p->bprog_HL)) {
+                CK(cudaMalloc(&p->d_bprog, bprog.size() * sizeof(uint32_t)));
+                CK(cudaMemcpy(p->d_bprog, bprog.data(), bprog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            }
         }
         if (p->fast_kernel == 2) {
             std::vector<uint32_t> units;
@@ -319,7 +320,7 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_idx) cudaFree(plan->d_idx);
         if (plan->d_runs) cudaFree(plan->d_runs);
         if (plan->d_units) cudaFree(plan->d_units);
-        if (plan->d_adv) cudaFree(plan->d_adv);
+        if (plan->d_bprog) cudaFree(plan->d_bprog);
     }
     delete plan;
     return SK_OK;

@@ -35,7 +35,7 @@ double smolyak_leaf_flops(const sk_plan &plan);
 
 // ---- Smolyak with a K×nvec coefficient block: on-chip collocation tiles × Θ with FP64 DMMA (sk_block.cu)
 bool smolyak_block_supported(const sk_plan &plan);
-void smolyak_block_program(const sk_plan &plan, std::vector<uint8_t> &adv);
+bool smolyak_block_program(const sk_plan &plan, std::vector<uint32_t> &prog, int *F, int *HL);
 cudaError_t smolyak_block_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
                                   double *out, cudaStream_t stream);
 double smolyak_block_flops(const sk_plan &plan, int nvec);
