@@ -22,7 +22,8 @@
 //                   loads pipeline and the DMULs issue back to back.
 //   phase B         4 × 16 terms of DMMA: 8 warps, warp tile 32 points × NVT/4 vectors, accumulators in
 //                   registers, A fragments from the phase-A tile, B fragments from the Θ ring.
-//   loader warp     (asynchronous to the phases) streams 16×NVT slabs of Θ — rows are contiguous in the
+//   loader warp     (asynchronous to the phases; its warpgroup runs at 40 registers so that the workers get
+//                   232, see setmaxnreg below) streams 16×NVT slabs of Θ — rows are contiguous in the
 //                   caller's layout — with the bulk-copy engine (cp.async.bulk + mbarrier complete_tx)
 //                   into rows padded to NVT+4 doubles (conflict-free fragment loads), and the factor
 //                   program of the next 64 terms.  Θ (159 MB at cfg 5) is read by all CTAs in the same
@@ -45,6 +46,7 @@ constexpr int kPT = 64;              // points per tile
 constexpr int kKA = 64;              // terms per phase-A chunk
 constexpr int kKC = 16;              // terms per Θ stage
 constexpr int kNS = 3;               // Θ stages
+constexpr int kGT = 8;               // terms a thread forms together in phase A (independent products in flight)
 constexpr int kWorkers = 8;          // worker warps (phase A and DMMA)
 constexpr int kLDP = kPT + 4;        // ≡ 4 (mod 16) doubles: conflict-free A fragments
 constexpr uint32_t kHigh = 0x80000000u;   // factor lives in the global scratch
@@ -96,7 +98,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // factor-program geometry shared by host and device: FP slots (4 or 8 words) per term, then one 16-byte
-// trailer per 64-term chunk (word 0: bit g set = group g of 4 terms has a factor in the global scratch)
+// trailer per 64-term chunk (word 0: bit g set = group g of kGT terms has a factor in the global scratch)
 __host__ __device__ constexpr int slots_padded(int F) { return F <= 4 ? 4 : 8; }
 __host__ __device__ constexpr int prog_chunk_words(int F) { return kKA * slots_padded(F) + 4; }
 
@@ -135,7 +137,7 @@ __device__ __forceinline__ double term_value(const uint32_t *slot, const char *t
 }
 
 template <int F, int NVT, int WM, int WN>
-__global__ void __launch_bounds__((kWorkers + 1) * 32, 1) smolyak_block_kernel(const __grid_constant__ BlockParams q) {
+__global__ void __launch_bounds__((kWorkers + 4) * 32, 1) smolyak_block_kernel(const __grid_constant__ BlockParams q) {
     static_assert(WM * WN == kWorkers, "eight worker warps");
     using L = BlockSmem<NVT>;
     constexpr int LDB = L::LDB;
@@ -165,6 +167,9 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, 1) smolyak_block_kernel(c
     uint32_t pit = 0;                                     // program chunk counter
 
     if (warp < kWorkers) {
+        // two worker warpgroups at 232 registers: setmaxnreg moves registers between whole warpgroups of a CTA
+        // (the register file is per scheduler: with a third full-size warp there, everyone is capped at 168)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int wm = warp / WN, wn = warp % WN;
         const int g = lane >> 2, t = lane & 3;
         const int pt = threadIdx.x & (kPT - 1), qd = threadIdx.x / kPT;       // phase A: point, quarter of the chunk
@@ -207,26 +212,26 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, 1) smolyak_block_kernel(c
                 const uint32_t himask = pg[kKA * FP];
                 if (!(q.dbg & 2)) {
 #pragma unroll
-                    for (int grp = 0; grp < 4; grp++) {
-                        const int r0 = qd * 16 + grp * 4;
-                        uint32_t slot[4][FP];
+                    for (int grp = 0; grp < 16 / kGT; grp++) {
+                        const int r0 = qd * 16 + grp * kGT;
+                        uint32_t slot[kGT][FP];
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
+                        for (int u = 0; u < kGT; u++)
 #pragma unroll
                             for (int w = 0; w < FP; w += 4) {
                                 const uint4 v = *reinterpret_cast<const uint4 *>(pg + (r0 + u) * FP + w);
                                 slot[u][w] = v.x; slot[u][w + 1] = v.y; slot[u][w + 2] = v.z; slot[u][w + 3] = v.w;
                             }
-                        double a[4];
-                        if ((himask >> (qd * 4 + grp)) & 1u) {
+                        double a[kGT];
+                        if ((himask >> (qd * (16 / kGT) + grp)) & 1u) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) a[u] = term_value<F, true>(slot[u], tabp, reinterpret_cast<const char *>(scr));
+                            for (int u = 0; u < kGT; u++) a[u] = term_value<F, true>(slot[u], tabp, reinterpret_cast<const char *>(scr));
                         } else {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) a[u] = term_value<F, false>(slot[u], tabp, nullptr);
+                            for (int u = 0; u < kGT; u++) a[u] = term_value<F, false>(slot[u], tabp, nullptr);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; u++) As[(r0 + u) * kLDP + pt] = a[u];
+                        for (int u = 0; u < kGT; u++) As[(r0 + u) * kLDP + pt] = a[u];
                     }
                 }
                 __syncwarp();
@@ -284,7 +289,10 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, 1) smolyak_block_kernel(c
             }
         }
     } else {
-        // ------------------------------------------------------------------ loader warp
+        // ------------------------------------------------------------------ loader warpgroup: gives its registers
+        // to the workers (128·(168−40) = 2·128·(232−168)); one warp streams Θ and the program, three retire
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp > kWorkers) return;
         constexpr uint32_t chunk_bytes = (uint32_t)prog_chunk_words(F) * 4;
         auto load_prog = [&](int64_t ch, uint32_t pi) {
             const int pb = pi & 1;
@@ -338,7 +346,7 @@ cudaError_t launch_block(const BlockParams &q0, int grid, int rows, cudaStream_t
     if (e != cudaSuccess) return e;
     q.n_vtiles = (q.nvec + NVT - 1) / NVT;
     const int64_t tiles = q.n_ptiles * q.n_vtiles;
-    kern<<<(int)std::min<int64_t>(tiles, grid), (kWorkers + 1) * 32, smem, stream>>>(q);
+    kern<<<(int)std::min<int64_t>(tiles, grid), (kWorkers + 4) * 32, smem, stream>>>(q);
     count_launch();
     return cudaGetLastError();
 }
@@ -394,7 +402,7 @@ bool smolyak_block_program(const sk_plan &plan, std::vector<uint32_t> &prog, int
                 if (i <= HL) sl[nf++] = (uint32_t)((2 + j * (HL - 1) + (i - 2)) * kPT * 8);
                 else {
                     sl[nf++] = kHigh | (uint32_t)((j * (S.H - HL) + (i - HL - 1)) * kPT * 8);
-                    blk[kKA * FP] |= 1u << (r / 4);
+                    blk[kKA * FP] |= 1u << (r / kGT);
                 }
             }
         }
