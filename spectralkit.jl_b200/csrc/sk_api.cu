@@ -307,6 +307,11 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
             p->n_units = (int64_t)units.size();
             CK(cudaMalloc(&p->d_units, units.size() * sizeof(uint32_t)));
             CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            std::vector<uint32_t> thmap;
+            p->theta_slots = skk::smolyak_leaf_theta_map(*p, &thmap);
+            if ((int64_t)thmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
+            CK(cudaMalloc(&p->d_thmap, thmap.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(p->d_thmap, thmap.data(), thmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
     }
     *out = p.release();
@@ -320,6 +325,7 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_idx) cudaFree(plan->d_idx);
         if (plan->d_runs) cudaFree(plan->d_runs);
         if (plan->d_units) cudaFree(plan->d_units);
+        if (plan->d_thmap) cudaFree(plan->d_thmap);
         if (plan->d_bprog) cudaFree(plan->d_bprog);
     }
     delete plan;

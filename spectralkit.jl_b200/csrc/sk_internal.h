@@ -70,6 +70,8 @@ struct sk_plan {
     int64_t n_runs = 0;
     uint32_t *d_units = nullptr; // [n_units] r | carry << 8             (unrolled-leaf kernel)
     int64_t n_units = 0;
+    uint32_t *d_thmap = nullptr; // [K] shared-memory slot of every coefficient (unrolled-leaf kernel)
+    int64_t theta_slots = 0;
     uint32_t *d_bprog = nullptr; // factor program of the coefficient-block kernel (sk_block.cu)
     int bprog_F = 0, bprog_HL = 0;
     int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves

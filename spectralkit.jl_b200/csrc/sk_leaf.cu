@@ -28,6 +28,50 @@ static int leaf_depth(const sk_plan &plan) {
     return 0;
 }
 
+// shared-memory slot of every coefficient: mirrors leaf_end / LeafBlocks of sk_leaf_impl.cuh (pair-aligned blocks
+// wherever a runtime loop changes the base); returns the slot after the last coefficient of Leaf<T, R>
+static int leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
+                        std::vector<uint32_t> *map) {
+    if (T == 0 || R == 0) { if (map) map->push_back((uint32_t)(base + off)); return off + 1; }
+    off = leaf_map_rec(S, blk_of, LOOPD, T - 1, R, off, base, map);
+    if (T < LOOPD) {
+        for (int64_t i = 2; i <= S.ell[(size_t)R]; i++) {
+            const int b = blk_of[(size_t)i];
+            if (R - b == 0) { if (map) map->push_back((uint32_t)(base + off)); off++; }
+            else off = leaf_map_rec(S, blk_of, LOOPD, T - 1, R - b, off, base, map);
+        }
+    } else {
+        for (int B = 1; B <= R; B++) {
+            const int cnt = (int)(S.ell[(size_t)B] - S.ell[(size_t)B - 1]);
+            if (R - B == 0) {
+                if (map) for (int c = 0; c < cnt; c++) map->push_back((uint32_t)(base + off + c));
+                off = even_up(off + cnt);
+            } else {
+                const int start = even_up(off);
+                const int CS = even_up(leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, 0, nullptr));
+                if (map) for (int c = 0; c < cnt; c++) leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, base + start + (int64_t)c * CS, map);
+                off = start + cnt * CS;
+            }
+        }
+    }
+    return off;
+}
+
+// θ scatter map of the whole plan (units in traversal order, each starting an aligned block); returns the slot count
+int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) {
+    const skh::SmolyakSet &S = plan.set;
+    const int LL = leaf_depth(plan);
+    const int LOOPD = leaf_loopd_c(LL, plan.fast_mode == 1);
+    std::vector<int> blk_of((size_t)S.H + 2, S.M);
+    for (int b = S.M - 1; b >= 0; b--) for (int64_t i = 1; i <= S.ell[(size_t)b]; i++) blk_of[(size_t)i] = b;
+    std::vector<uint32_t> units;
+    smolyak_leaf_units(plan, units);
+    if (map) { map->clear(); map->reserve((size_t)S.K); }
+    int64_t pos = 0;
+    for (uint32_t w : units) pos += even_up(leaf_map_rec(S, blk_of, LOOPD, LL, (int)(w & 0xFF), 0, pos, map));
+    return pos;
+}
+
 bool smolyak_leaf_supported(const sk_plan &plan) {
     if (plan.basis.kind != SK_BASIS_SMOLYAK || plan.fast_mode < 0) return false;
     if (plan.basis.M != plan.basis.B) return false;            // block cap below the budget: generic kernel
@@ -35,11 +79,11 @@ bool smolyak_leaf_supported(const sk_plan &plan) {
     if (LL < 1) return false;
     const int d = plan.basis.d, nup = d - LL;
     if (nup > 12) return false;
-    std::vector<uint32_t> units;
     int64_t n_units = 1;
     if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
+    if (n_units * 2 + plan.K > 64 * 1024) return false;        // cannot fit anyway (and keeps the map cheap)
     const bool g = plan.fast_mode == 1;
-    const LeafSmem lay(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, plan.K);
+    const LeafSmem lay(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, smolyak_leaf_theta_map(plan, nullptr));
     return lay.total <= 200 * 1024;                              // θ must fit in shared memory next to the rest
 }
 
@@ -118,8 +162,8 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, const
     if (n == 0) return cudaSuccess;
     const int d = plan.basis.d, LL = leaf_depth(plan), nup = d - LL;
     LeafParams q{};
-    q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units;
-    q.n = n; q.K = plan.K; q.n_units = plan.n_units; q.D = d; q.nup = nup;
+    q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
+    q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }

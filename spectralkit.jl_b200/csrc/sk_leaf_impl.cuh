@@ -53,6 +53,45 @@ __host__ __device__ constexpr long nterms(int T, int R) {
     return s;
 }
 
+// ---- θ in shared memory is read in PAIRS.  Coefficients are consumed strictly in traversal order, so inside
+// straight-line code every even slot is one LDS.128 that also delivers the next coefficient (halves the
+// shared-memory instructions of the kernel: one per coefficient was half of all LSU traffic).  Slots are
+// offsets from a 16-byte aligned block start and are compile-time constants after inlining.  Wherever a
+// runtime loop changes the base, blocks are re-aligned to even slots (leaf_end is the layout; the host
+// mirrors it in smolyak_leaf_theta_map to scatter θ into shared memory).
+struct ThRd {
+    const double *base;
+    double hold;
+};
+__device__ __forceinline__ double th_get(ThRd &t, int off) {
+    if ((off & 1) == 0) {
+        const double2 v = *reinterpret_cast<const double2 *>(t.base + off);
+        t.hold = v.y;
+        return v.x;
+    }
+    return t.hold;
+}
+__host__ __device__ constexpr int even_up(int x) { return (x + 1) & ~1; }
+// slot after the last coefficient of Leaf<T, R> when it starts at slot `off` (LOOPD: first dimension walked by runtime loops)
+template <int GK>
+__host__ __device__ constexpr int leaf_end(int LOOPD, int T, int R, int off) {
+    if (T == 0 || R == 0) return off + 1;
+    off = leaf_end<GK>(LOOPD, T - 1, R, off);
+    if (T < LOOPD) {
+        for (int i = 2; i <= ellc<GK>(R); i++) {
+            const int b = blockof<GK>(i);
+            off = R - b == 0 ? off + 1 : leaf_end<GK>(LOOPD, T - 1, R - b, off);
+        }
+    } else {
+        for (int B = 1; B <= R; B++) {
+            const int cnt = ellc<GK>(B) - ellc<GK>(B - 1);
+            if (R - B == 0) off = even_up(off + cnt);
+            else off = even_up(off) + cnt * even_up(leaf_end<GK>(LOOPD, T - 1, R - B, 0));
+        }
+    }
+    return off;
+}
+
 constexpr int kTab = 6;              // table entries: indices 2..7 (degrees 1..6)
 
 template <bool GRAD>
@@ -103,8 +142,8 @@ struct Leaf;
 template <int GK, int T, int R, class CX, int I>
 struct LeafStep {
     static constexpr bool GRAD = CX::GRAD;
-    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value],
-                                               double &Tc, double &Tq, double &dTc, double &dTq) {
+    static __device__ __forceinline__ int run(const CX &cx, ThRd &th, int off, double (&a)[NC<GRAD, T>::value],
+                                              double &Tc, double &Tq, double &dTc, double &dTq) {
         if constexpr (I <= ellc<GK>(R)) {
             constexpr int b = blockof<GK>(I);
             double Tv, dTv = 0.0;
@@ -124,13 +163,13 @@ struct LeafStep {
             if constexpr (R - b == 0) {
                 // no budget left below: the child is the single coefficient θ (all lower indices are 1,
                 // every lower partial is structurally zero)
-                const double c0 = *th;
-                th += 1;
+                const double c0 = th_get(th, off);
+                off += 1;
                 if (GRAD) a[GRAD ? T : 0] = fma(dTv, c0, a[GRAD ? T : 0]);
                 a[0] = fma(Tv, c0, a[0]);
             } else {
                 double c[NC<GRAD, T - 1>::value];
-                Leaf<GK, T - 1, R - b, CX>::run(cx, th, c);
+                off = Leaf<GK, T - 1, R - b, CX>::run(cx, th, off, c);
                 if (GRAD) {
                     a[GRAD ? T : 0] = fma(dTv, c[0], a[GRAD ? T : 0]);
 #pragma unroll
@@ -138,7 +177,9 @@ struct LeafStep {
                 }
                 a[0] = fma(Tv, c[0], a[0]);
             }
-            LeafStep<GK, T, R, CX, I + 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
+            return LeafStep<GK, T, R, CX, I + 1>::run(cx, th, off, a, Tc, Tq, dTc, dTq);
+        } else {
+            return off;
         }
     }
 };
@@ -149,10 +190,15 @@ struct LeafStep {
 template <int GK, int T, int R, class CX, int B>
 struct LeafBlocks {
     static constexpr bool GRAD = CX::GRAD;
-    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value],
-                                               double &Tc, double &Tq, double &dTc, double &dTq) {
+    static __device__ __forceinline__ int run(const CX &cx, ThRd &th, int off, double (&a)[NC<GRAD, T>::value],
+                                              double &Tc, double &Tq, double &dTc, double &dTq) {
         if constexpr (B <= R) {
             constexpr int lo = ellc<GK>(B - 1) + 1, hi = ellc<GK>(B);
+            // θ of this block: single coefficients are contiguous scalars; multi-term children each start an
+            // aligned block of CS slots (same layout as leaf_end)
+            constexpr int CS = R - B == 0 ? 1 : even_up(leaf_end<GK>(CX::LOOPD, T - 1, R - B > 0 ? R - B : 0, 0));
+            const int start = R - B == 0 ? off : even_up(off);
+            const double *blk = th.base + start;
             const double2 *tb = cx.stab + (size_t)(T - 1 - CX::TREG) * (kTab + 1) * CX::NT;
             double x2 = 0, x2d = 0;
             if constexpr (hi > kTab + 1) {
@@ -175,13 +221,13 @@ struct LeafBlocks {
                     dTq = dTc; dTc = dTv; Tq = Tc; Tc = Tv;
                 }
                 if constexpr (R - B == 0) {
-                    const double c0 = *th;
-                    th += 1;
+                    const double c0 = blk[i - lo];
                     if (GRAD) a[GRAD ? T : 0] = fma(dTv, c0, a[GRAD ? T : 0]);
                     a[0] = fma(Tv, c0, a[0]);
                 } else {
                     double c[NC<GRAD, T - 1>::value];
-                    Leaf<GK, T - 1, R - B, CX>::run(cx, th, c);
+                    ThRd sub{blk + (i - lo) * CS, 0.0};
+                    Leaf<GK, T - 1, R - B, CX>::run(cx, sub, 0, c);
                     if (GRAD) {
                         a[GRAD ? T : 0] = fma(dTv, c[0], a[GRAD ? T : 0]);
 #pragma unroll
@@ -190,16 +236,18 @@ struct LeafBlocks {
                     a[0] = fma(Tv, c[0], a[0]);
                 }
             }
-            LeafBlocks<GK, T, R, CX, B + 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
+            return LeafBlocks<GK, T, R, CX, B + 1>::run(cx, th, even_up(start + (hi - lo + 1) * CS), a, Tc, Tq, dTc, dTq);
+        } else {
+            return off;
         }
     }
 };
 
 template <int GK, int R, class CX>
 struct Leaf<GK, 0, R, CX> {
-    static __device__ __forceinline__ void run(const CX &, const double *&th, double (&a)[1]) {
-        a[0] = *th;
-        th += 1;
+    static __device__ __forceinline__ int run(const CX &, ThRd &th, int off, double (&a)[1]) {
+        a[0] = th_get(th, off);
+        return off + 1;
     }
 };
 
@@ -207,19 +255,19 @@ template <int GK, int T, int R, class CX>
 struct Leaf {
     static constexpr bool GRAD = CX::GRAD;
     // a[0] = Σ θ·Π T, a[m] = ∂/∂y_m (m = 1..T) over {(i_1..i_T): Σ b_j <= R}; consumes θ in traversal order
-    static __device__ __forceinline__ void run(const CX &cx, const double *&th, double (&a)[NC<GRAD, T>::value]) {
+    static __device__ __forceinline__ int run(const CX &cx, ThRd &th, int off, double (&a)[NC<GRAD, T>::value]) {
         if constexpr (R == 0) {
-            a[0] = *th;
-            th += 1;
+            a[0] = th_get(th, off);
             if (GRAD) {
 #pragma unroll
                 for (int m = 1; m <= T; m++) a[GRAD ? m : 0] = 0.0;
             }
+            return off + 1;
         } else {
             if constexpr (CX::SYNCT > 0 && nterms<GK>(T, R) >= CX::SYNCT && nterms<GK>(T - 1, R) < CX::SYNCT) __syncthreads();
             {   // index 1: T_0 = 1, derivative 0
                 double c[NC<GRAD, T - 1>::value];
-                Leaf<GK, T - 1, R, CX>::run(cx, th, c);
+                off = Leaf<GK, T - 1, R, CX>::run(cx, th, off, c);
                 a[0] = c[0];
                 if (GRAD) {
 #pragma unroll
@@ -228,8 +276,8 @@ struct Leaf {
                 }
             }
             double Tc = 0, Tq = 0, dTc = 0, dTq = 0;
-            if constexpr (T < CX::LOOPD) LeafStep<GK, T, R, CX, 2>::run(cx, th, a, Tc, Tq, dTc, dTq);
-            else LeafBlocks<GK, T, R, CX, 1>::run(cx, th, a, Tc, Tq, dTc, dTq);
+            if constexpr (T < CX::LOOPD) return LeafStep<GK, T, R, CX, 2>::run(cx, th, off, a, Tc, Tq, dTc, dTq);
+            else return LeafBlocks<GK, T, R, CX, 1>::run(cx, th, off, a, Tc, Tq, dTc, dTq);
         }
     }
 };
@@ -240,7 +288,8 @@ struct LeafParams {
     double *out;
     const double *theta;
     const uint32_t *units;        // r | carry << 8
-    int64_t n, K, n_units;
+    const uint32_t *thmap;        // shared-memory slot of every coefficient (pair-aligned blocks, see leaf_end)
+    int64_t n, K, n_units, Kslots;
     int D, nup;
     sk_transform tr[SK_MAX_DIM];
 };
@@ -266,13 +315,13 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
     const int tid = threadIdx.x;
     const int D = q.D, NUP = q.nup;
     const int NF = F_ACC + D + 1;
-    const LeafSmem lay(NT, LL, TREG, D, NUP, q.n_units, q.K);
+    const LeafSmem lay(NT, LL, TREG, D, NUP, q.n_units, q.Kslots);
     double2 *stab = reinterpret_cast<double2 *>(smem_raw + lay.stab) + tid;
     double *up = reinterpret_cast<double *>(smem_raw + lay.up);           // [NUP][NF][threads]
     uint32_t *s_units = reinterpret_cast<uint32_t *>(smem_raw + lay.units);
     double *s_theta = reinterpret_cast<double *>(smem_raw + lay.theta);
     for (int64_t i = tid; i < q.n_units; i += NT) s_units[i] = q.units[i];
-    for (int64_t i = tid; i < q.K; i += NT) s_theta[i] = q.theta[i];
+    for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i];
     __syncthreads();
 #define UP(u, f) up[((size_t)(u) * NF + (f)) * NT + tid]
     constexpr int NCL = NC<GRAD, LL>::value;
@@ -320,18 +369,18 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
             if (GRAD) { UP(u, F_X1) = xj[GRAD ? 1 : 0]; UP(u, F_X2D) = 2.0 * xj[GRAD ? 1 : 0]; }
         }
         uint32_t first = 0xFFFFFFFFu;                       // bit u: upper level u sits at index 1
-        const double *th = s_theta;
+        const double *ub = s_theta;                         // aligned block of the current unit
         double a[NCL];
         for (int64_t un = 0; un < q.n_units; un++) {
             const uint32_t w = s_units[un];
             const int r = (int)(w & 0xFF), c = (int)(w >> 8);
             switch (r) {
-            case 0: Leaf<GK, LL, 0, CX>::run(cx, th, a); break;
-            case 1: if constexpr (RMAX >= 1) Leaf<GK, LL, RMAX >= 1 ? 1 : 0, CX>::run(cx, th, a); break;
-            case 2: if constexpr (RMAX >= 2) Leaf<GK, LL, RMAX >= 2 ? 2 : 0, CX>::run(cx, th, a); break;
-            case 3: if constexpr (RMAX >= 3) Leaf<GK, LL, RMAX >= 3 ? 3 : 0, CX>::run(cx, th, a); break;
-            case 4: if constexpr (RMAX >= 4) Leaf<GK, LL, RMAX >= 4 ? 4 : 0, CX>::run(cx, th, a); break;
-            case 5: if constexpr (RMAX >= 5) Leaf<GK, LL, RMAX >= 5 ? 5 : 0, CX>::run(cx, th, a); break;
+            case 0: { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, 0, CX>::run(cx, th, 0, a)); } break;
+            case 1: if constexpr (RMAX >= 1) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 1 ? 1 : 0, CX>::run(cx, th, 0, a)); } break;
+            case 2: if constexpr (RMAX >= 2) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 2 ? 2 : 0, CX>::run(cx, th, 0, a)); } break;
+            case 3: if constexpr (RMAX >= 3) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 3 ? 3 : 0, CX>::run(cx, th, 0, a)); } break;
+            case 4: if constexpr (RMAX >= 4) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 4 ? 4 : 0, CX>::run(cx, th, 0, a)); } break;
+            case 5: if constexpr (RMAX >= 5) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 5 ? 5 : 0, CX>::run(cx, th, 0, a)); } break;
             default: break;
             }
             if (NUP > 0) {
@@ -396,7 +445,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
 template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
     auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT>;
-    const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.K);
+    const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.Kslots);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -436,14 +485,9 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
         const int v = e ? atoi(e) : 0;
         if (LL == 6 && v > 0) {
             switch (v) {
-            case 1: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0, 99, 256>(q, stream);
-            case 2: return launch_leaf<GK, 6, 4, GRAD, 3, 2, 0, 99, 256>(q, stream);
-            case 3: return launch_leaf<GK, 6, 4, GRAD, 4, 2, 0, 6, 256>(q, stream);
-            case 4: return launch_leaf<GK, 6, 4, GRAD, 3, 3, 0, 99, 256>(q, stream);
-            case 5: return launch_leaf<GK, 6, 4, GRAD, 4, 4, 0, 99, 128>(q, stream);
-            case 6: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 99, 512>(q, stream);
-            case 7: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 99, 512>(q, stream);
-            case 8: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 99, 768>(q, stream);
+            case 1: return launch_leaf<GK, 6, 4, GRAD, 1, 1, 0, 6, 384>(q, stream);
+            case 2: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 5, 384>(q, stream);
+            case 3: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 5, 256>(q, stream);
             }
         }
     }
