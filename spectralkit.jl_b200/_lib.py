@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspectralkit_b200.so")
+LIB_PATH = os.environ.get("SK_B200_LIB") or os.path.join(_HERE, "lib", "libspectralkit_b200.so")   # override: tuning builds
 
 SK_OK, SK_ERR_ARGUMENT, SK_ERR_DOMAIN, SK_ERR_UNSUPPORTED, SK_ERR_CUDA, SK_ERR_NO_DEVICE, SK_ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 SK_BASIS_CHEBYSHEV, SK_BASIS_SMOLYAK = 0, 1

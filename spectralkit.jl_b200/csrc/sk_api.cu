@@ -3,6 +3,7 @@
 // No evaluation happens on the host: every hot-path entry point fails if there is no device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -34,6 +35,20 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+void workspace_destroy(sk_workspace *w) {
+    if (!w) return;
+    cudaFree(w->theta);
+    for (int i = 0; i < sk_workspace::NBUF; i++) {
+        cudaFree(w->xb[i]); cudaFree(w->ob[i]);
+        if (w->in[i]) cudaEventDestroy((cudaEvent_t)w->in[i]);
+        if (w->done[i]) cudaEventDestroy((cudaEvent_t)w->done[i]);
+        if (w->outc[i]) cudaEventDestroy((cudaEvent_t)w->outc[i]);
+    }
+    if (w->e0) cudaEventDestroy((cudaEvent_t)w->e0);
+    for (int i = 0; i < 3; i++) if (w->s[i]) cudaStreamDestroy((cudaStream_t)w->s[i]);
+    delete w;
+}
 
 bool valid_grid_kind(int g) { return g == SK_GRID_INTERIOR || g == SK_GRID_ENDPOINT || g == SK_GRID_INTERIOR2; }
 
@@ -326,6 +341,8 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_runs) cudaFree(plan->d_runs);
         if (plan->d_units) cudaFree(plan->d_units);
         if (plan->d_thmap) cudaFree(plan->d_thmap);
+        for (sk_workspace *w : plan->ws_free) workspace_destroy(w);
+        plan->ws_free.clear();
         if (plan->d_bprog) cudaFree(plan->d_bprog);
     }
     delete plan;
@@ -373,6 +390,56 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
     return SK_OK;
 }
 
+// points per chunk of the host-buffer pipeline (SK_HOST_CHUNK overrides; experiments)
+int64_t host_chunk_points() {
+    static const int64_t v = [] { const char *e = getenv("SK_HOST_CHUNK"); int64_t x = e ? atoll(e) : 0; return x > 0 ? x : (int64_t)1 << 21; }();
+    return v;
+}
+
+// borrows a staging workspace from the plan for the duration of one call
+struct WorkspaceLease {
+    const sk_plan *plan;
+    sk_workspace *ws = nullptr;
+    explicit WorkspaceLease(const sk_plan *p) : plan(p) {
+        std::lock_guard<std::mutex> lk(plan->ws_mu);
+        if (!plan->ws_free.empty()) { ws = plan->ws_free.back(); plan->ws_free.pop_back(); }
+    }
+    ~WorkspaceLease() {
+        if (!ws) return;
+        std::unique_lock<std::mutex> lk(plan->ws_mu);
+        if (plan->ws_free.size() < 2) { plan->ws_free.push_back(ws); return; }
+        lk.unlock();
+        workspace_destroy(ws);
+    }
+    int ensure(size_t theta_bytes, size_t x_bytes, size_t o_bytes) {
+        if (!ws) {
+            ws = new (std::nothrow) sk_workspace();
+            if (!ws) SK_FAIL(SK_ERR_ARGUMENT, "out of memory");
+            for (int i = 0; i < 3; i++) CK(cudaStreamCreateWithFlags((cudaStream_t *)&ws->s[i], cudaStreamNonBlocking));
+            for (int i = 0; i < sk_workspace::NBUF; i++) {
+                CK(cudaEventCreateWithFlags((cudaEvent_t *)&ws->in[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags((cudaEvent_t *)&ws->done[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags((cudaEvent_t *)&ws->outc[i], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags((cudaEvent_t *)&ws->e0, cudaEventDisableTiming));
+        }
+        if (theta_bytes > ws->theta_cap) { cudaFree(ws->theta); ws->theta = nullptr; ws->theta_cap = 0; CK(cudaMalloc(&ws->theta, theta_bytes)); ws->theta_cap = theta_bytes; }
+        if (x_bytes > ws->x_cap) {
+            for (int i = 0; i < sk_workspace::NBUF; i++) { cudaFree(ws->xb[i]); ws->xb[i] = nullptr; }
+            ws->x_cap = 0;
+            for (int i = 0; i < sk_workspace::NBUF; i++) CK(cudaMalloc(&ws->xb[i], x_bytes));
+            ws->x_cap = x_bytes;
+        }
+        if (o_bytes > ws->o_cap) {
+            for (int i = 0; i < sk_workspace::NBUF; i++) { cudaFree(ws->ob[i]); ws->ob[i] = nullptr; }
+            ws->o_cap = 0;
+            for (int i = 0; i < sk_workspace::NBUF; i++) CK(cudaMalloc(&ws->ob[i], o_bytes));
+            ws->o_cap = o_bytes;
+        }
+        return SK_OK;
+    }
+};
+
 int check_lincomb_args(const sk_plan *plan, const double *theta, int64_t theta_len, int nvec, const double *x,
                        int64_t n, double *out) {
     if (!plan) SK_FAIL(SK_ERR_ARGUMENT, "plan is NULL");
@@ -399,58 +466,40 @@ int sk_linear_combination(const sk_plan *plan, const double *theta, int64_t thet
     const int Eout = nvec > 1 ? nvec : plan->E;
     if (flags & SK_MEM_DEVICE) return run_lincomb_device(plan, theta, nvec, x, n, out, exact, stream);
 
-    // host buffers: θ once, then points in chunks through a 2-deep pipeline
-    // (H2D copy of chunk i+1 and D2H copy of chunk i-1 overlap the kernel of chunk i when the
-    // caller's buffers are pinned; pageable buffers still work, the copies just serialise)
-    const size_t theta_bytes = (size_t)plan->K * nvec * sizeof(double);
-    double *d_theta = nullptr;
-    CK(cudaMalloc(&d_theta, theta_bytes));
-    struct Cleanup {
-        double *theta; double *xb[2] = {nullptr, nullptr}; double *ob[2] = {nullptr, nullptr};
-        cudaStream_t s[3] = {nullptr, nullptr, nullptr}; cudaEvent_t in[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, outc[2] = {nullptr, nullptr};
-        ~Cleanup() {
-            cudaFree(theta);
-            for (int i = 0; i < 2; i++) { cudaFree(xb[i]); cudaFree(ob[i]); if (in[i]) cudaEventDestroy(in[i]); if (done[i]) cudaEventDestroy(done[i]); if (outc[i]) cudaEventDestroy(outc[i]); }
-            for (int i = 0; i < 3; i++) if (s[i]) cudaStreamDestroy(s[i]);
-        }
-    } c{d_theta};
+    // host buffers: θ once, then points in chunks through a 3-deep pipeline: the H2D copy of chunk i+1 and the
+    // D2H copy of chunk i-1 overlap the kernel of chunk i when the caller's buffers are pinned (pageable
+    // buffers still work, the copies just serialise).  PCIe is full duplex: the bound is max(in, out) bytes.
     if (n == 0) return SK_OK;
-    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 22);
-    const int nbuf = n > chunk ? 2 : 1;
-    for (int i = 0; i < nbuf; i++) {
-        CK(cudaMalloc(&c.xb[i], (size_t)chunk * d * sizeof(double)));
-        CK(cudaMalloc(&c.ob[i], (size_t)chunk * Eout * sizeof(double)));
-        CK(cudaEventCreateWithFlags(&c.in[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.outc[i], cudaEventDisableTiming));
-    }
-    for (int i = 0; i < 3; i++) CK(cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking));
-    cudaStream_t s_in = c.s[0], s_k = c.s[1], s_out = c.s[2];
+    const size_t theta_bytes = (size_t)plan->K * nvec * sizeof(double);
+    const int64_t chunk = std::min<int64_t>(n, host_chunk_points());
+    WorkspaceLease lease(plan);
+    rc = lease.ensure(theta_bytes, (size_t)chunk * d * sizeof(double), (size_t)chunk * Eout * sizeof(double));
+    if (rc != SK_OK) return rc;
+    sk_workspace &w = *lease.ws;
+    constexpr int NB = sk_workspace::NBUF;
+    cudaStream_t s_in = (cudaStream_t)w.s[0], s_k = (cudaStream_t)w.s[1], s_out = (cudaStream_t)w.s[2];
     // order after work already queued on the caller's stream
-    cudaEvent_t e0;
-    CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-    CK(cudaEventRecord(e0, stream));
-    CK(cudaStreamWaitEvent(s_in, e0, 0));
-    CK(cudaStreamWaitEvent(s_k, e0, 0));
-    CK(cudaEventDestroy(e0));
-    CK(cudaMemcpyAsync(d_theta, theta, theta_bytes, cudaMemcpyHostToDevice, s_in));
+    CK(cudaEventRecord((cudaEvent_t)w.e0, stream));
+    CK(cudaStreamWaitEvent(s_in, (cudaEvent_t)w.e0, 0));
+    CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.e0, 0));
+    CK(cudaMemcpyAsync(w.theta, theta, theta_bytes, cudaMemcpyHostToDevice, s_k));
     int64_t done_pts = 0;
     for (int it = 0; done_pts < n; it++) {
-        const int b = it % nbuf;
+        const int b = it % NB;
         const int64_t m = std::min<int64_t>(chunk, n - done_pts);
-        if (it >= nbuf) {                                   // buffer reuse: wait until its results left
-            CK(cudaStreamWaitEvent(s_in, c.done[b], 0));    // kernel that read xb[b] finished
-            CK(cudaStreamWaitEvent(s_k, c.outc[b], 0));     // D2H that read ob[b] finished
+        if (it >= NB) {                                                   // buffer reuse
+            CK(cudaStreamWaitEvent(s_in, (cudaEvent_t)w.done[b], 0));     // the kernel that read xb[b] finished
+            CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.outc[b], 0));      // the D2H copy that read ob[b] finished
         }
-        CK(cudaMemcpyAsync(c.xb[b], x + (size_t)done_pts * d, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice, s_in));
-        CK(cudaEventRecord(c.in[b], s_in));
-        CK(cudaStreamWaitEvent(s_k, c.in[b], 0));
-        rc = run_lincomb_device(plan, d_theta, nvec, c.xb[b], m, c.ob[b], exact, s_k);
-        if (rc != SK_OK) return rc;
-        CK(cudaEventRecord(c.done[b], s_k));
-        CK(cudaStreamWaitEvent(s_out, c.done[b], 0));
-        CK(cudaMemcpyAsync(out + (size_t)done_pts * Eout, c.ob[b], (size_t)m * Eout * sizeof(double), cudaMemcpyDeviceToHost, s_out));
-        CK(cudaEventRecord(c.outc[b], s_out));
+        CK(cudaMemcpyAsync(w.xb[b], x + (size_t)done_pts * d, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        CK(cudaEventRecord((cudaEvent_t)w.in[b], s_in));
+        CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.in[b], 0));
+        rc = run_lincomb_device(plan, (const double *)w.theta, nvec, (const double *)w.xb[b], m, (double *)w.ob[b], exact, s_k);
+        if (rc != SK_OK) { cudaDeviceSynchronize(); return rc; }
+        CK(cudaEventRecord((cudaEvent_t)w.done[b], s_k));
+        CK(cudaStreamWaitEvent(s_out, (cudaEvent_t)w.done[b], 0));
+        CK(cudaMemcpyAsync(out + (size_t)done_pts * Eout, w.ob[b], (size_t)m * Eout * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        CK(cudaEventRecord((cudaEvent_t)w.outc[b], s_out));
         done_pts += m;
     }
     CK(cudaStreamSynchronize(s_out));

@@ -2,6 +2,7 @@
 // (sk_kernels.cu) and the C-ABI layer (sk_api.cu).  Not part of the public boundary.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,19 @@ bool partials_canonical(int d, int np, const int32_t *partials, std::vector<int3
 
 }  // namespace skh
 
+// ---- staging for calls with HOST buffers: device chunk buffers, streams and events of the copy/compute pipeline.
+// A call borrows one from its plan (creating it on first use) and returns it, so repeated calls do not pay
+// cudaMalloc/cudaFree (which also synchronise the device); concurrent calls on one plan get one each.
+struct sk_workspace {
+    static constexpr int NBUF = 3;
+    void *theta = nullptr; size_t theta_cap = 0;
+    void *xb[NBUF] = {}, *ob[NBUF] = {};
+    size_t x_cap = 0, o_cap = 0;              // bytes per buffer
+    void *s[3] = {};                           // cudaStream_t: H2D, kernels, D2H
+    void *in[NBUF] = {}, *done[NBUF] = {}, *outc[NBUF] = {};   // cudaEvent_t
+    void *e0 = nullptr;
+};
+
 // ---- the plan object behind the opaque handle
 struct sk_plan {
     sk_basis_desc basis{};       // normalised (M clamped to B)
@@ -76,4 +90,7 @@ struct sk_plan {
     int bprog_F = 0, bprog_HL = 0;
     int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves
     double flops_fast = 0, flops_direct = 0;
+    // host-buffer staging pool (the only mutable state of a plan; guarded by ws_mu)
+    mutable std::mutex ws_mu;
+    mutable std::vector<sk_workspace *> ws_free;
 };

@@ -484,10 +484,9 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
         const char *e = getenv("SK_LEAF_VARIANT");
         const int v = e ? atoi(e) : 0;
         if (LL == 6 && v > 0) {
-            switch (v) {
-            case 1: return launch_leaf<GK, 6, 4, GRAD, 1, 1, 0, 6, 384>(q, stream);
-            case 2: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 5, 384>(q, stream);
-            case 3: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 5, 256>(q, stream);
+            switch (v) {      // NB: LOOPD must equal leaf_loopd_c (the host's coefficient map depends on it)
+            case 1: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 6, 352>(q, stream);
+            case 2: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 6, 256>(q, stream);
             }
         }
     }
