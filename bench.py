@@ -255,7 +255,7 @@ def run_ours(args):
             pass
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["smolyak_nested_dram_bytes_per_point"] * n
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["leaf_dram_bytes_per_point"] * n   # ncu, per launch of n points
         except Exception:
             pass
         line = {

@@ -332,14 +332,15 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
     for (int64_t p0 = (int64_t)blockIdx.x * NT; p0 < q.n; p0 += (int64_t)gridDim.x * NT) {
         const bool live = p0 + tid < q.n;
         const int64_t p = live ? p0 + tid : q.n - 1;
-        const double *xp = q.x + p * D;
+        const double *xp = q.x + p * D;                      // points and results are streamed (ld.cs / st.cs): they must not
+                                                              // evict the spill lines, which live in L2
         using CX = LeafCtx<GRAD, TREG, FENCE, LOOPD, NT>;
         CX cx;
         cx.stab = stab;
 #pragma unroll
         for (int j = 0; j < LL; j++) {
             double xj[GRAD ? 2 : 1];
-            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[j], xp[j], xj);
+            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[j], __ldcs(xp + j), xj);
             const double x0 = xj[0], x1 = GRAD ? xj[GRAD ? 1 : 0] : 0.0;
             double t[kTab], dt[kTab];
             const double x2 = 2.0 * x0, x2d = 2.0 * x1;
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
         }
         for (int u = 0; u < NUP; u++) {
             double xj[GRAD ? 2 : 1];
-            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[LL + u], xp[LL + u], xj);
+            skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[LL + u], __ldcs(xp + LL + u), xj);
             UP(u, F_X0) = xj[0]; UP(u, F_X2) = 2.0 * xj[0];
             if (GRAD) { UP(u, F_X1) = xj[GRAD ? 1 : 0]; UP(u, F_X2D) = 2.0 * xj[GRAD ? 1 : 0]; }
         }
@@ -432,10 +433,10 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
         double *o = q.out + p * E;
         if (live) {
             if (NUP > 0) {
-                for (int m = 0; m < E; m++) o[m] = UP(NUP - 1, F_ACC + m);
+                for (int m = 0; m < E; m++) __stcs(o + m, UP(NUP - 1, F_ACC + m));
             } else {
 #pragma unroll
-                for (int m = 0; m < NCL; m++) o[m] = a[m];
+                for (int m = 0; m < NCL; m++) __stcs(o + m, a[m]);
             }
         }
     }
