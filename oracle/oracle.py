@@ -333,4 +333,10 @@ def smolyak_basis_at(grid_kind, d, B, M, y, trs=None, spec=None, ext2=False):
 
 
 def max_threads():
-    return lib().orc_max_threads()
+    """Host threads the oracle may use: the CPUs this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which would otherwise make the timed CPU baseline single-threaded), never below OpenMP's own default."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        avail = os.cpu_count() or 1
+    return max(int(lib().orc_max_threads()), avail)

@@ -260,9 +260,10 @@ struct DirectParams {
     int8_t orders[SK_MAX_COMP][SK_MAX_DIM];
 };
 
+// tables of one tile: thread (tid, ty) builds the dimensions j ≡ ty (mod ny) of point tid
 template <int EMAX>
-__device__ __forceinline__ void build_tables(const DirectParams &q, const double *xp, bool live, double *tab, int P, int tid) {
-    for (int j = 0; j < q.d; j++) {
+__device__ __forceinline__ void build_tables(const DirectParams &q, const double *xp, bool live, double *tab, int P, int tid, int ty, int ny) {
+    for (int j = ty; j < q.d; j += ny) {
         double xj[EMAX];
         skd::to_pm1_jet<EMAX>(q.tr[j], live ? xp[j] : 0.0, xj);
         Jet<EMAX> X, fp = skd::jet_one<EMAX>(), fpp, f = fp;
@@ -288,40 +289,38 @@ __device__ __forceinline__ double term_product(const DirectParams &q, const uint
     return b;
 }
 
-template <int EMAX, int NCMAX>
+// Block = P points (x) × ny component lanes (y).  The sequential sum s = s + θ_k·b_k of one component of one
+// point is one thread's job (the reference's order), but components — and coefficient vectors — are
+// independent, so they run on different threads: the tables limit a CTA to P = 32..128 points, and this is
+// what fills the SM with warps.  A warp is 32 consecutive points of one component: table reads stay conflict
+// free and the index table / θ reads stay warp-uniform.
+template <int EMAX>
 __global__ void smolyak_direct_lincomb_kernel(const __grid_constant__ DirectParams q) {
     extern __shared__ double tab[];
-    const int P = blockDim.x, tid = threadIdx.x;
+    const int P = blockDim.x, tid = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
     const int nc = q.ncomp ? q.ncomp : 1;
     for (int64_t p0 = (int64_t)blockIdx.x * P; p0 < q.n; p0 += (int64_t)gridDim.x * P) {
         const int64_t p = p0 + tid;
         const bool live = p < q.n;
+        __syncthreads();                                   // the previous tile's tables are no longer read
+        build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid, ty, ny);
         __syncthreads();
-        build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid);
-        // (each thread only reads its own column: no barrier needed after the build)
         if (q.nvec == 1) {
-            double s[NCMAX];
-            for (int64_t k = 0; k < q.K; k++) {
-                const uint16_t *ik = q.idx + (size_t)k * q.d;
-                double th = q.theta[k];
-#pragma unroll
-                for (int c = 0; c < NCMAX; c++)
-                    if (c < nc) {
-                        double b = term_product<EMAX>(q, ik, c, tab, P, tid);
-                        s[c] = k == 0 ? th * b : s[c] + th * b;
-                    }
+            for (int c = ty; c < nc; c += ny) {
+                double s = 0.0;
+                for (int64_t k = 0; k < q.K; k++) {
+                    const double b = term_product<EMAX>(q, q.idx + (size_t)k * q.d, c, tab, P, tid);
+                    const double th = q.theta[k];
+                    s = k == 0 ? th * b : s + th * b;      // generic_api.jl:114-128: mul then add, never fused
+                }
+                if (live) q.out[(size_t)p * nc + c] = s;
             }
-            if (live)
-#pragma unroll
-                for (int c = 0; c < NCMAX; c++)
-                    if (c < nc) q.out[(size_t)p * nc + c] = s[c];
         } else {
             // SVector coefficients: plain points only (checked by the API layer); 8 vectors per pass
-            for (int v0 = 0; v0 < q.nvec; v0 += 8) {
+            for (int v0 = ty * 8; v0 < q.nvec; v0 += ny * 8) {
                 double s[8];
                 for (int64_t k = 0; k < q.K; k++) {
-                    const uint16_t *ik = q.idx + (size_t)k * q.d;
-                    double b = term_product<EMAX>(q, ik, 0, tab, P, tid);
+                    const double b = term_product<EMAX>(q, q.idx + (size_t)k * q.d, 0, tab, P, tid);
                     const double *tk = q.theta + (size_t)k * q.nvec + v0;
 #pragma unroll
                     for (int v = 0; v < 8; v++)
@@ -347,7 +346,7 @@ __global__ void smolyak_direct_basis_kernel(const __grid_constant__ DirectParams
     double *stage = smem + (size_t)q.d * q.H * EMAX * P;
     const int64_t p0 = (int64_t)blockIdx.x * P, p = p0 + tid;
     const bool live = p < q.n, full = p0 + P <= q.n;
-    build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid);
+    build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid, 0, 1);
     const int64_t k0 = (int64_t)blockIdx.y * q.k_chunk, k1 = min(q.K, k0 + q.k_chunk);
     int buf = 0;
     for (int64_t k = k0; k < k1; k++) {
@@ -403,21 +402,24 @@ cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int
     q.theta = theta; q.nvec = nvec; q.x = x; q.out = out; q.n = n; q.ld = n; q.k_chunk = q.K;
     const int emax = plan_emax(plan);
     size_t per_point = (size_t)q.d * q.H * emax * sizeof(double);
+    // independent sums per point: components, or groups of 8 coefficient vectors
+    const int lanes_wanted = nvec > 1 ? (nvec + 7) / 8 : (q.ncomp ? q.ncomp : 1);
     int P = pick_points_per_block(per_point, 200 * 1024);
     if (!P) return cudaErrorInvalidConfiguration;
+    if (lanes_wanted == 1 && n <= (int64_t)P * sm_count() / 2) while (P > 32 && n <= (int64_t)(P / 2) * sm_count()) P >>= 1;   // few points: more, smaller tiles
+    int ny = std::max(1, std::min(lanes_wanted, 1024 / P));
     size_t smem = per_point * P;
     int grid = (int)std::min<int64_t>((n + P - 1) / P, (int64_t)sm_count() * 8);
     cudaError_t e = cudaSuccess;
-#define SK_LAUNCH_DL(EM, NC)                                                             \
+#define SK_LAUNCH_DL(EM)                                                                 \
     do {                                                                                 \
-        e = set_smem(smolyak_direct_lincomb_kernel<EM, NC>, smem);                       \
-        if (e == cudaSuccess) smolyak_direct_lincomb_kernel<EM, NC><<<grid, P, smem, stream>>>(q); \
+        cudaFuncAttributes fa;                                                           \
+        e = cudaFuncGetAttributes(&fa, smolyak_direct_lincomb_kernel<EM>);               \
+        if (e == cudaSuccess) ny = std::max(1, std::min(ny, 65536 / std::max(fa.numRegs, 1) / P));   /* register file */ \
+        if (e == cudaSuccess) e = set_smem(smolyak_direct_lincomb_kernel<EM>, smem);     \
+        if (e == cudaSuccess) smolyak_direct_lincomb_kernel<EM><<<grid, dim3(P, ny), smem, stream>>>(q); \
     } while (0)
-    const int nc = q.ncomp ? q.ncomp : 1;
-    if (emax == 1) { if (nc <= 1) SK_LAUNCH_DL(1, 1); else if (nc <= 8) SK_LAUNCH_DL(1, 8); else SK_LAUNCH_DL(1, 64); }
-    else if (emax == 2) { if (nc <= 8) SK_LAUNCH_DL(2, 8); else if (nc <= 24) SK_LAUNCH_DL(2, 24); else SK_LAUNCH_DL(2, 64); }
-    else if (emax == 3) { if (nc <= 8) SK_LAUNCH_DL(3, 8); else if (nc <= 24) SK_LAUNCH_DL(3, 24); else SK_LAUNCH_DL(3, 64); }
-    else { if (nc <= 8) SK_LAUNCH_DL(6, 8); else SK_LAUNCH_DL(6, 64); }
+    if (emax == 1) SK_LAUNCH_DL(1); else if (emax == 2) SK_LAUNCH_DL(2); else if (emax == 3) SK_LAUNCH_DL(3); else SK_LAUNCH_DL(6);
 #undef SK_LAUNCH_DL
     if (e != cudaSuccess) return e;
     count_launch();
