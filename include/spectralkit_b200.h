@@ -168,6 +168,14 @@ int sk_transform_to(const sk_transform *tr, int d, int order, int allow_rational
 int sk_transform_from(const sk_transform *tr, int d, const double *x, int64_t n, double *out,
                       uint32_t flags, int device, void *stream);
 
+/* ---------------------------------------------------------------- fitting (initialisation time) */
+/* θ = collocation_matrix(basis) \ y on the basis' own grid (docs/src/index.md:92, test/test_smolyak.jl:20-21,
+ * test/test_generic_api.jl:20).  The collocation matrix is generated on the device by the basis_at kernels; the
+ * dense LU (partial pivoting, as Julia's `\` on a square matrix) is cuSOLVER's, loaded on first use.  The plan must
+ * carry no derivative request.  y and theta: [K][nrhs], nrhs fastest (the layout of Vector{SVector{nrhs}}; nrhs = 1
+ * is a plain vector).  SK_ERR_ARGUMENT if the matrix is singular (Julia: SingularException).  Synchronises `stream`. */
+int sk_collocation_solve(const sk_plan *plan, const double *y, int nrhs, double *theta, uint32_t flags, void *stream);
+
 /* ---------------------------------------------------------------- multi-GPU (one process, G devices) */
 /* Points are independent: contiguous slices of ceil(n/G) points per device, plans replicated,
  * θ copied to each device, no reduction, outputs land in the caller's host buffer.

@@ -670,6 +670,26 @@ def collocation_matrix(basis, x=None, **kw):
     return basis_at(basis, x, **kw)
 
 
+def collocation_solve(basis, y, *, device: int = 0):
+    """θ = `collocation_matrix(basis) \\ y` on the basis' own grid (docs/src/index.md:92,
+    test/test_smolyak.jl:20-21): y holds the function values at `grid(basis)`, shape (K,) or (K, M) for M
+    functions at once; returns θ of the same shape.  The matrix is generated and factorised on the GPU."""
+    on_device = _is_torch(y) and y.is_cuda
+    dev = y.device.index if on_device else None
+    plan = get_plan(basis, 0, None, dev if dev is not None else device)
+    if on_device:
+        yy = y.to(dtype=torch.float64).contiguous()
+    else:
+        yy = np.ascontiguousarray(y.cpu().numpy() if _is_torch(y) else y, dtype=np.float64)
+    if yy.ndim not in (1, 2) or int(yy.shape[0]) != plan.info.K:
+        raise ArgumentError("y must hold one value (or one fixed-length vector) per grid point of the basis")
+    nrhs = 1 if yy.ndim == 1 else int(yy.shape[1])
+    out = torch.empty_like(yy) if on_device else np.empty_like(yy)
+    flags = L.SK_MEM_DEVICE if on_device else L.SK_MEM_HOST
+    L.check(L.lib.sk_collocation_solve(plan.handle, _ptr(yy), nrhs, _ptr(out), flags, _stream(dev)))
+    return out
+
+
 def _transform_common(to, dom_or_basis, t, x, device):
     ts = list(t) if isinstance(t, CoordinateTransformations) else [t]
     order = 0

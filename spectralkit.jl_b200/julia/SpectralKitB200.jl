@@ -164,6 +164,26 @@ function collocation_matrix_gpu(basis, xs::Vector{<:Union{NTuple{N,Float64},SVec
 end
 const basis_at_gpu = collocation_matrix_gpu
 
+# ---- fitting: θ = collocation_matrix(basis) \ y on the basis' own grid (docs/src/index.md:92) ----
+"`collocation_matrix(basis) \\ y` with the matrix generated and factorised on the GPU; `y` are the values at `grid(basis)`."
+function collocation_solve_gpu(basis, y::Vector{Float64})
+    p = plan_for(basis)
+    length(y) == p.K || throw(ArgumentError("length(y) == dimension(basis) must hold."))
+    θ = similar(y)
+    GC.@preserve y θ check(ccall((:sk_collocation_solve, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, UInt32, Ptr{Cvoid}), p.handle, y, 1, θ, SK_MEM_HOST, C_NULL))
+    θ
+end
+function collocation_solve_gpu(basis, y::Vector{SVector{M,Float64}}) where {M}
+    p = plan_for(basis)
+    length(y) == p.K || throw(ArgumentError("length(y) == dimension(basis) must hold."))
+    θ = similar(y)
+    GC.@preserve y θ check(ccall((:sk_collocation_solve, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, UInt32, Ptr{Cvoid}),
+        p.handle, Ptr{Float64}(pointer(y)), M, Ptr{Float64}(pointer(θ)), SK_MEM_HOST, C_NULL))
+    θ
+end
+
 # ---- metadata that must be bit-exact (SURVEY.md §8(b)) -------------------------------------------
 "collect(grid(basis)) computed by the library (correctly rounded sinpi/cospi); compare with `collect(grid(basis))`."
 function grid_gpu_library(basis)

@@ -416,6 +416,43 @@ def test_smolyak_block_transformed_cfg5_shape(orc):
     np.testing.assert_allclose(sk.linear_combination(basis @ ct, th2, y), g8 @ w, rtol=1e-9, atol=1e-9 * np.abs(scale[:, :8]).max())
 
 
+# ---- §8(f) rank 1: fit on the basis' own grid, θ = collocation_matrix(basis) \ y, then evaluate
+def test_collocation_solve_smolyak_roundtrip(orc):
+    import torch
+    rng = np.random.default_rng(808)
+    trs = [mk_tr(orc, 1, 0, 4), mk_tr(orc, 2, 1, 2), mk_tr(orc, 3, 0, 4)]
+    ct = sk.coordinate_transformations(*[t[0] for t in trs])
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), 3) @ ct
+    K = sk.dimension(basis)
+    g = np.asarray(sk.grid(basis))
+    f = lambda y: np.stack([np.exp(-y[:, 0] / 4) * (y[:, 1] - 1) / (y[:, 1] + 1) + np.tanh(y[:, 2] / 4),
+                            1.0 / (1.0 + y[:, 0]) + 0.3 * np.tanh(y[:, 2] / 3) ** 2,
+                            np.cos(y[:, 0]) / (y[:, 1] + 2)], axis=1)
+    Y = f(g)                                                    # three functions at once: (K, 3)
+    theta = sk.collocation_solve(basis, Y)
+    assert theta.shape == (K, 3)
+    C = sk.collocation_matrix(basis)                            # bit-identical to the oracle (tested above)
+    want = np.linalg.solve(C, Y)                                # LAPACK getrf/getrs = Julia's `\` on a square matrix
+    tol = 50 * np.linalg.cond(C) * np.finfo(float).eps
+    assert np.max(np.abs(theta - want)) <= tol * np.max(np.abs(want))
+    # interpolation property (test/test_smolyak.jl:20-30): the fit reproduces the values at the grid
+    back = sk.linear_combination(basis, theta, g)
+    np.testing.assert_allclose(back, Y, rtol=0, atol=1e-9 * np.abs(Y).max())
+    # one right-hand side, device-resident
+    th1 = sk.collocation_solve(basis, torch.as_tensor(Y[:, 0].copy()).cuda())
+    assert th1.is_cuda and np.max(np.abs(th1.cpu().numpy() - want[:, 0])) <= tol * np.max(np.abs(want))
+
+
+def test_collocation_solve_univariate_and_errors(orc):
+    b = sk.Chebyshev(sk.EndpointGrid(), 20) @ sk.BoundedLinear(-2, 3)
+    g = np.asarray(sk.grid(b))
+    theta = sk.collocation_solve(b, np.exp(g / 3))
+    x = np.linspace(-2, 3, 101)
+    np.testing.assert_allclose(sk.linear_combination(b, theta, x), np.exp(x / 3), atol=1e-13, rtol=1e-12)
+    with pytest.raises(sk.ArgumentError):
+        sk.collocation_solve(b, np.ones(19))
+
+
 def test_golden_fixtures(orc):
     g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
     b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
