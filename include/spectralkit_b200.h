@@ -141,6 +141,17 @@ int sk_grid(const sk_basis_desc *basis, const sk_transform *tr, double *out);
 int sk_partials_canonical(int d, int np, const int32_t *partials, int32_t *out_orders, int cap,
                           int32_t *ncomp, int32_t *degrees);
 
+/* ---------------------------------------------------------------- refinement between bases (host; index merge) */
+/* is_subset_basis(basis1, basis2) (chebyshev.jl:140-142, smolyak_api.jl:141-153, generic_api.jl:254,314-317):
+ * tr1/tr2 NULL for untransformed bases; transformed bases need identical transformations. */
+int sk_is_subset_basis(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2,
+                       const sk_transform *tr2, int *out);
+/* augment_coefficients(basis1, basis2, θ1) (chebyshev.jl:133-138, smolyak_api.jl:155-208, generic_api.jl:319-322):
+ * θ2[dimension(basis2)][nvec] gets θ1's entries at the shared indices (one ordered pass, the reference's
+ * PaddingIterator) and zeros elsewhere.  SK_ERR_ARGUMENT unless is_subset_basis and theta1_len == dimension(basis1). */
+int sk_augment_coefficients(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2,
+                            const sk_transform *tr2, const double *theta1, int64_t theta1_len, int nvec, double *theta2);
+
 /* ---------------------------------------------------------------- plans */
 /* tr: NULL (untransformed basis) or 1 (Chebyshev) / d (Smolyak) transformations: basis ∘ t
  * (generic_api.jl:263-274).  spec: NULL = values only. */

@@ -213,6 +213,27 @@ def naive_indices(kind, d, B, M):
     return out
 
 
+def augment_coefficients(kind, d, B1, M1, B2, M2, theta1):
+    """src/smolyak_api.jl:155-208 — PaddingIterator: one pass over the traversal of the larger basis; the smaller
+    traversal advances only on a match and, once exhausted, never matches again (sentinel (0, 0, …))."""
+    it1 = naive_indices(kind, d, B1, M1)
+    it2 = naive_indices(kind, d, B2, M2)
+    assert len(theta1) == len(it1)
+    out, i = [], 0
+    cur = it1[0] if it1 else None
+    for ix in it2:
+        if cur is not None and ix == cur:
+            out.append(theta1[i])
+            if i + 1 < len(it1):
+                i += 1
+                cur = it1[i]
+            else:
+                cur = None
+        else:
+            out.append(0.0 * theta1[0])
+    return out
+
+
 def shuffle_by_blocks(kind, b):
     """test/test_smolyak_traversal.jl:38-52 — block-by-block set differences of nested grids."""
     def g(bb):

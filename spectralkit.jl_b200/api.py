@@ -670,6 +670,42 @@ def collocation_matrix(basis, x=None, **kw):
     return basis_at(basis, x, **kw)
 
 
+def _desc_and_tr(basis):
+    base, trs = _split(basis)
+    return base._desc(), (_tr_array(trs) if trs is not None else None)
+
+
+def is_subset_basis(basis1, basis2) -> bool:
+    """Can coefficients of `basis1` be augmented to `basis2`? (generic_api.jl:247-254, chebyshev.jl:140-142,
+    smolyak_api.jl:141-153, generic_api.jl:314-317)"""
+    for b in (basis1, basis2):
+        if not isinstance(_split(b)[0], (Chebyshev, SmolyakBasis)):
+            return False
+    d1, t1 = _desc_and_tr(basis1)
+    d2, t2 = _desc_and_tr(basis2)
+    if (t1 is None) != (t2 is None) or (t1 is not None and len(t1) != len(t2)):
+        return False
+    out = C.c_int(0)
+    L.check(L.lib.sk_is_subset_basis(C.byref(d1), t1, C.byref(d2), t2, C.byref(out)))
+    return bool(out.value)
+
+
+def augment_coefficients(basis1, basis2, theta1):
+    """Coefficients θ2 of `basis2` with `linear_combination(basis1, θ1, x) == linear_combination(basis2, θ2, x)`
+    (generic_api.jl:229-242; chebyshev.jl:133-138; smolyak_api.jl:155-208).  θ1: (K1,) or (K1, M)."""
+    if not is_subset_basis(basis1, basis2):
+        raise ArgumentError("is_subset_basis(basis1, basis2) must hold.")
+    th = np.ascontiguousarray(theta1.cpu().numpy() if _is_torch(theta1) else theta1, dtype=np.float64)
+    if th.ndim not in (1, 2):
+        raise ArgumentError("θ must be a vector of reals or of fixed-length vectors")
+    nvec = 1 if th.ndim == 1 else int(th.shape[1])
+    d1, t1 = _desc_and_tr(basis1)
+    d2, t2 = _desc_and_tr(basis2)
+    out = np.empty((dimension(basis2),) + th.shape[1:], dtype=np.float64)
+    L.check(L.lib.sk_augment_coefficients(C.byref(d1), t1, C.byref(d2), t2, _ptr(th), int(th.shape[0]), nvec, _ptr(out)))
+    return out
+
+
 def collocation_solve(basis, y, *, device: int = 0):
     """θ = `collocation_matrix(basis) \\ y` on the basis' own grid (docs/src/index.md:92,
     test/test_smolyak.jl:20-21): y holds the function values at `grid(basis)`, shape (K,) or (K, M) for M

@@ -232,6 +232,70 @@ int sk_partials_canonical(int d, int np, const int32_t *partials, int32_t *out_o
     return SK_OK;
 }
 
+// ------------------------------------------------------------------------------ refinement (host, index merge)
+namespace {
+bool same_transforms(const sk_transform *a, const sk_transform *b, int d) {
+    if (!a || !b) return a == b;                                    // a transformed and a plain basis never match
+    for (int j = 0; j < d; j++)
+        if (a[j].kind != b[j].kind || std::memcmp(&a[j].p0, &b[j].p0, sizeof(double)) != 0 || std::memcmp(&a[j].p1, &b[j].p1, sizeof(double)) != 0) return false;
+    return true;
+}
+// is_subset_basis (chebyshev.jl:140-142, smolyak_api.jl:141-153, generic_api.jl:254,314-317)
+bool subset_basis(const sk_basis_desc &a, const sk_transform *ta, const sk_basis_desc &b, const sk_transform *tb) {
+    if (a.kind != b.kind) return false;
+    const int d = a.kind == SK_BASIS_CHEBYSHEV ? 1 : a.d;
+    if (a.kind == SK_BASIS_SMOLYAK && a.d != b.d) return false;
+    if (!same_transforms(ta, tb, d)) return false;
+    if (a.kind == SK_BASIS_CHEBYSHEV) return b.N >= a.N;             // grid kinds may differ
+    return b.B >= a.B && b.M >= a.M && a.grid_kind == b.grid_kind;   // shared univariate indices need the same nested family
+}
+}  // namespace
+
+int sk_is_subset_basis(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2, int *out) {
+    sk_basis_desc a, b;
+    int rc = normalise_basis(basis1, &a);
+    if (rc != SK_OK) return rc;
+    rc = normalise_basis(basis2, &b);
+    if (rc != SK_OK) return rc;
+    if (!out) SK_FAIL(SK_ERR_ARGUMENT, "out is NULL");
+    *out = subset_basis(a, tr1, b, tr2) ? 1 : 0;
+    return SK_OK;
+}
+
+int sk_augment_coefficients(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2,
+                            const double *theta1, int64_t theta1_len, int nvec, double *theta2) {
+    sk_basis_desc a, b;
+    int rc = normalise_basis(basis1, &a);
+    if (rc != SK_OK) return rc;
+    rc = normalise_basis(basis2, &b);
+    if (rc != SK_OK) return rc;
+    if (!theta1 || !theta2 || nvec < 1) SK_FAIL(SK_ERR_ARGUMENT, "bad buffers");
+    if (!subset_basis(a, tr1, b, tr2)) SK_FAIL(SK_ERR_ARGUMENT, "is_subset_basis(basis1, basis2) must hold.");          // smolyak_api.jl:203
+    const size_t w = (size_t)nvec;
+    if (a.kind == SK_BASIS_CHEBYSHEV) {                                                                       // chebyshev.jl:133-138
+        if (theta1_len != a.N) SK_FAIL(SK_ERR_ARGUMENT, "length(θ1) == dimension(basis1) must hold.");
+        std::memcpy(theta2, theta1, (size_t)a.N * w * sizeof(double));
+        std::memset(theta2 + (size_t)a.N * w, 0, (size_t)(b.N - a.N) * w * sizeof(double));
+        return SK_OK;
+    }
+    skh::SmolyakSet S1, S2;
+    if (!skh::smolyak_enumerate(a.grid_kind, a.d, a.B, a.M, S1) || !skh::smolyak_enumerate(b.grid_kind, b.d, b.B, b.M, S2))
+        SK_FAIL(SK_ERR_ARGUMENT, "cannot enumerate index set");
+    if (theta1_len != S1.K) SK_FAIL(SK_ERR_ARGUMENT, "dimension(basis1) == length(θ1) must hold.");                // smolyak_api.jl:204
+    // PaddingIterator (smolyak_api.jl:155-200): one pass over the larger traversal, the smaller one advancing
+    // only on a match; after its last element nothing matches any more
+    const size_t d = (size_t)a.d;
+    int64_t i1 = 0;
+    for (int64_t k = 0; k < S2.K; k++) {
+        double *dst = theta2 + (size_t)k * w;
+        if (i1 < S1.K && std::memcmp(&S1.idx[(size_t)i1 * d], &S2.idx[(size_t)k * d], d * sizeof(uint16_t)) == 0) {
+            std::memcpy(dst, theta1 + (size_t)i1 * w, w * sizeof(double));
+            i1++;
+        } else std::memset(dst, 0, w * sizeof(double));
+    }
+    return SK_OK;
+}
+
 // ------------------------------------------------------------------------------ plans
 int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_deriv_spec *spec, int device,
                    sk_plan **out) {

@@ -453,6 +453,23 @@ def test_collocation_solve_univariate_and_errors(orc):
         sk.collocation_solve(b, np.ones(19))
 
 
+def test_augmented_coefficients_evaluate_equally(orc):
+    # test/test_smolyak.jl:70-79 and test/test_chebyshev.jl:46-54: same function on the refined basis
+    rng = np.random.default_rng(919)
+    b1 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3, 2), 4)
+    b2 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4, 4), 4)
+    th1 = rng.standard_normal(sk.dimension(b1))
+    th2 = sk.augment_coefficients(b1, b2, th1)
+    x = rand_pm1(rng, (500, 4))
+    assert same(sk.linear_combination(b1, th1, x, exact=True), orc.smolyak_lincomb(2, 4, 3, 2, th1, x))
+    np.testing.assert_allclose(sk.linear_combination(b2, th2, sk.gradient(4)(x)), sk.linear_combination(b1, th1, sk.gradient(4)(x)), rtol=1e-12, atol=1e-12)
+    t = sk.BoundedLinear(-2, 3)
+    c1, c2 = sk.Chebyshev(sk.InteriorGrid(), 7) @ t, sk.Chebyshev(sk.EndpointGrid(), 12) @ t
+    th = rng.standard_normal(7)
+    y = rng.uniform(-2, 3, 300)
+    np.testing.assert_allclose(sk.linear_combination(c2, sk.augment_coefficients(c1, c2, th), y), sk.linear_combination(c1, th, y), rtol=1e-13, atol=1e-13)
+
+
 def test_golden_fixtures(orc):
     g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
     b20 = sk.Chebyshev(sk.InteriorGrid(), 20)

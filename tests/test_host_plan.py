@@ -209,3 +209,45 @@ def test_basis_constructors_and_api_surface():
     assert sk.partial(1, 0).partials == ((1,),)
     with pytest.raises(sk.ArgumentError):
         sk.partial((1, 0))
+
+
+# ---- refinement between bases: is_subset_basis / augment_coefficients (host index merge through the C ABI)
+def test_is_subset_basis_rules():
+    cheb = lambda g, n: sk.Chebyshev(g, n)
+    assert sk.is_subset_basis(cheb(sk.InteriorGrid(), 5), cheb(sk.EndpointGrid(), 6))          # test/test_chebyshev.jl:63-65
+    assert not sk.is_subset_basis(cheb(sk.InteriorGrid(), 5), cheb(sk.InteriorGrid(), 4))      # :67-68
+    sm = lambda g, B, M, d=2: sk.smolyak_basis(sk.Chebyshev, g, sk.SmolyakParameters(B, M), d)
+    b1 = sm(sk.InteriorGrid(), 2, 2)
+    assert not sk.is_subset_basis(b1, sm(sk.EndpointGrid(), 2, 3))                              # test/test_smolyak.jl:60-63 (after the M clamp: B2 = 2, M2 = 2, other grid)
+    assert not sk.is_subset_basis(b1, sm(sk.InteriorGrid(), 2, 1))                              # :65-68
+    assert sk.is_subset_basis(b1, sm(sk.InteriorGrid(), 3, 2))                                  # :70-71
+    assert not sk.is_subset_basis(b1, sm(sk.InteriorGrid(), 3, 2, d=3))
+    assert not sk.is_subset_basis(b1, cheb(sk.InteriorGrid(), 50))
+    t, t2 = sk.SemiInfRational(0.3, 0.9), sk.SemiInfRational(0.3, 0.8)
+    assert sk.is_subset_basis(cheb(sk.InteriorGrid(), 5) @ t, cheb(sk.InteriorGrid(), 8) @ t)   # test/test_chebyshev.jl:75-82
+    assert not sk.is_subset_basis(cheb(sk.InteriorGrid(), 5) @ t, cheb(sk.InteriorGrid(), 8) @ t2)
+    assert not sk.is_subset_basis(cheb(sk.InteriorGrid(), 5) @ t, cheb(sk.InteriorGrid(), 8))
+    with pytest.raises(sk.ArgumentError):
+        sk.augment_coefficients(cheb(sk.InteriorGrid(), 5), cheb(sk.InteriorGrid(), 4), np.ones(5))
+    with pytest.raises(sk.ArgumentError):
+        sk.augment_coefficients(cheb(sk.InteriorGrid(), 5), cheb(sk.InteriorGrid(), 5), np.ones(4))   # too few coefficients (:70-71)
+
+
+@pytest.mark.parametrize("code,d,p1,p2", [(0, 2, (2, 2), (3, 2)), (2, 3, (2, 1), (4, 3)), (1, 2, (1, 1), (3, 3)), (2, 3, (0, 0), (2, 2)), (0, 2, (2, 2), (2, 2))])
+def test_augment_coefficients_matches_padding_iterator(code, d, p1, p2):
+    from oracle import py_oracle as po
+    grid = {0: sk.InteriorGrid(), 1: sk.EndpointGrid(), 2: sk.InteriorGrid2()}[code]
+    b1 = sk.smolyak_basis(sk.Chebyshev, grid, sk.SmolyakParameters(*p1), d)
+    b2 = sk.smolyak_basis(sk.Chebyshev, grid, sk.SmolyakParameters(*p2), d)
+    rng = np.random.default_rng(17)
+    th = rng.standard_normal(sk.dimension(b1))
+    want = np.array(po.augment_coefficients(code, d, p1[0], p1[1], p2[0], p2[1], list(th)))
+    got = sk.augment_coefficients(b1, b2, th)
+    assert got.shape == (sk.dimension(b2),) and (got == want).all()
+    assert np.count_nonzero(got) == np.count_nonzero(th)          # nothing lost: the smaller traversal is a subsequence
+    thv = rng.standard_normal((sk.dimension(b1), 3))                # SVector coefficients
+    gv = sk.augment_coefficients(b1, b2, thv)
+    for v in range(3):
+        assert (gv[:, v] == np.array(po.augment_coefficients(code, d, p1[0], p1[1], p2[0], p2[1], list(thv[:, v])))).all()
+    c = sk.augment_coefficients(sk.Chebyshev(grid, 4), sk.Chebyshev(grid, 9), np.arange(4.0))
+    assert (c == np.array([0, 1, 2, 3, 0, 0, 0, 0, 0.0])).all()
