@@ -431,6 +431,12 @@ int sk_plan_get_info(const sk_plan *plan, sk_plan_info *info) {
 // ------------------------------------------------------------------------------ evaluation
 namespace {
 
+// crossover with the DMMA kernel measured on B200 (profiles/r1_block_kernel.md); SK_LEAF_PER_VECTOR_MAX overrides (experiments)
+static int leaf_per_vector_max() {
+    static const int v = [] { const char *e = getenv("SK_LEAF_PER_VECTOR_MAX"); return e ? atoi(e) : 24; }();
+    return v;
+}
+
 // one device-resident evaluation on `stream`
 int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, const double *d_x, int64_t n,
                        double *d_out, bool exact, cudaStream_t stream) {
@@ -438,8 +444,9 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         CK(skk::uni_lincomb(plan->basis.N, plan->tr[0], plan->order, exact, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
-    if (!exact && nvec == 1 && plan->fast_kernel == 2) {
-        CK(skk::smolyak_leaf_lincomb(*plan, d_theta, d_x, n, d_out, stream));
+    // a few coefficient vectors: one unrolled-leaf launch per vector beats the 8-wide DMMA tile (values only)
+    if (!exact && plan->fast_kernel == 2 && (nvec == 1 || (nvec <= leaf_per_vector_max() && plan->fast_mode == 0))) {
+        CK(skk::smolyak_leaf_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
     if (!exact && nvec == 1 && plan->fast_kernel == 1) {

@@ -20,7 +20,7 @@
 //                   offsets of the table rows, built once from the traversal order,
 //                   smolyak_traversal.jl:211-231) replaces `__inc`; products are independent, so the
 //                   loads pipeline and the DMULs issue back to back.
-//   phase B         4 × 16 terms of DMMA: 8 warps, warp tile 32 points × NVT/4 vectors, accumulators in
+//   phase B         4 × 16 terms (wide tiles) of DMMA: 8 warps, warp tile 32 points × NVT/4 vectors, accumulators in
 //                   registers, A fragments from the phase-A tile, B fragments from the Θ ring.
 //   loader warp     (asynchronous to the phases; its warpgroup runs at 40 registers so that the workers get
 //                   232, see setmaxnreg below) streams 16×NVT slabs of Θ — rows are contiguous in the
@@ -44,7 +44,9 @@ namespace {
 
 constexpr int kPT = 64;              // points per tile
 constexpr int kKA = 64;              // terms per phase-A chunk
-constexpr int kKC = 16;              // terms per Θ stage
+// terms per Θ stage: 16 for wide vector tiles (a 3-stage ring of 33 KB slabs); narrow tiles stage more terms per
+// slab, otherwise the loop runs at the latency of one bulk copy per 16 terms (measured: 2.7 µs per 64 terms)
+__host__ __device__ constexpr int stage_terms(int NVT) { return NVT >= 128 ? 16 : NVT >= 64 ? 32 : 64; }
 constexpr int kNS = 3;               // Θ stages
 constexpr int kGT = 8;               // terms a thread forms together in phase A (independent products in flight)
 constexpr int kWorkers = 8;          // worker warps (phase A and DMMA)
@@ -106,7 +108,8 @@ template <int NVT>
 struct BlockSmem {
     static constexpr int LDB = NVT + 4;                       // ≡ 4 (mod 16) for NVT >= 16; rows stay 16-byte aligned
     static constexpr size_t a_bytes = (size_t)kKA * kLDP * 8;
-    static constexpr size_t b_stage = (size_t)kKC * LDB * 8;
+    static constexpr int KC = stage_terms(NVT);
+    static constexpr size_t b_stage = (size_t)KC * LDB * 8;
     static constexpr size_t prog_bytes = (size_t)prog_chunk_words(8) * 4;
     static constexpr size_t off_a = 0;
     static constexpr size_t off_b = off_a + a_bytes;
@@ -140,7 +143,7 @@ template <int F, int NVT, int WM, int WN>
 __global__ void __launch_bounds__((kWorkers + 4) * 32, 1) smolyak_block_kernel(const __grid_constant__ BlockParams q) {
     static_assert(WM * WN == kWorkers, "eight worker warps");
     using L = BlockSmem<NVT>;
-    constexpr int LDB = L::LDB;
+    constexpr int LDB = L::LDB, KC = L::KC;
     constexpr int WTM = kPT / WM, WTN = NVT / WN;         // warp tile
     constexpr int MT = WTM / 8, NT = WTN / 8;
     constexpr int FP = slots_padded(F);
@@ -239,10 +242,10 @@ __global__ void __launch_bounds__((kWorkers + 4) * 32, 1) smolyak_block_kernel(c
                 workers_sync();                               // the A tile is complete
                 // ---- phase B: 4 Θ stages of 16 terms
 #pragma unroll 1
-                for (int sub = 0; sub < kKA / kKC; sub++, it++) {
+                for (int sub = 0; sub < kKA / KC; sub++, it++) {
                     const int s = it % kNS;
                     mbar_wait(&full[s], (it / kNS) & 1);
-                    const double *Ap = As + sub * kKC * kLDP + wm * WTM + g;
+                    const double *Ap = As + sub * KC * kLDP + wm * WTM + g;
                     const double *Bp = reinterpret_cast<const double *>(smem + L::off_b + (size_t)s * L::b_stage) + wn * WTN + g;
                     if (!(q.dbg & 1)) {
                         double a[2][MT], b[2][NT];
@@ -251,8 +254,8 @@ __global__ void __launch_bounds__((kWorkers + 4) * 32, 1) smolyak_block_kernel(c
 #pragma unroll
                         for (int j = 0; j < NT; j++) b[0][j] = Bp[t * LDB + j * 8];
 #pragma unroll
-                        for (int kk = 0; kk < kKC / 4; kk++) {
-                            if (kk + 1 < kKC / 4) {           // fragments of the next k4 step fly while this one computes
+                        for (int kk = 0; kk < KC / 4; kk++) {
+                            if (kk + 1 < KC / 4) {           // fragments of the next k4 step fly while this one computes
 #pragma unroll
                                 for (int i = 0; i < MT; i++) a[(kk + 1) & 1][i] = Ap[((kk + 1) * 4 + t) * kLDP + i * 8];
 #pragma unroll
@@ -309,20 +312,20 @@ __global__ void __launch_bounds__((kWorkers + 4) * 32, 1) smolyak_block_kernel(c
             load_prog(0, pit);
             for (int64_t ch = 0; ch < n_chunks; ch++, pit++) {
                 if (ch + 1 < n_chunks) load_prog(ch + 1, pit + 1);
-                for (int sub = 0; sub < kKA / kKC; sub++, it++) {
+                for (int sub = 0; sub < kKA / KC; sub++, it++) {
                     const int s = it % kNS;
                     mbar_wait(&empty[s], ((it / kNS) & 1) ^ 1);
                     double *Bs = reinterpret_cast<double *>(smem + L::off_b + (size_t)s * L::b_stage);
-                    const int64_t k0 = ch * kKA + sub * kKC;
+                    const int64_t k0 = ch * kKA + sub * KC;
                     if (bulk) {
-                        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(kKC * cols * 8));
+                        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(KC * cols * 8));
                         __syncwarp();
-                        if (lane < kKC) {
-                            const int64_t k = min(k0 + lane, q.K - 1);   // rows past K: their A entries are exactly 0
-                            bulk_load(Bs + lane * LDB, q.theta + (size_t)k * q.nvec + v0, (uint32_t)(cols * 8), &full[s]);
+                        for (int r = lane; r < KC; r += 32) {
+                            const int64_t k = min(k0 + r, q.K - 1);      // rows past K: their A entries are exactly 0
+                            bulk_load(Bs + r * LDB, q.theta + (size_t)k * q.nvec + v0, (uint32_t)(cols * 8), &full[s]);
                         }
                     } else {
-                        for (int r = 0; r < kKC; r++) {
+                        for (int r = 0; r < KC; r++) {
                             const int64_t k = min(k0 + r, q.K - 1);
                             const double *src = q.theta + (size_t)k * q.nvec + v0;
                             for (int c = lane; c < cols; c += 32) Bs[r * LDB + c] = __ldg(src + c);

@@ -30,7 +30,7 @@ double smolyak_nested_flops(const sk_plan &plan);
 bool smolyak_leaf_supported(const sk_plan &plan);
 void smolyak_leaf_units(const sk_plan &plan, std::vector<uint32_t> &units);
 int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);
-cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n,
+cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
                                  double *out, cudaStream_t stream);
 double smolyak_leaf_flops(const sk_plan &plan);
 

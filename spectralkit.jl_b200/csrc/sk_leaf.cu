@@ -72,6 +72,9 @@ int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) 
     return pos;
 }
 
+static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
+                                            double *out, int64_t out_stride, cudaStream_t stream);
+
 bool smolyak_leaf_supported(const sk_plan &plan) {
     if (plan.basis.kind != SK_BASIS_SMOLYAK || plan.fast_mode < 0) return false;
     if (plan.basis.M != plan.basis.B) return false;            // block cap below the budget: generic kernel
@@ -157,12 +160,27 @@ double smolyak_leaf_flops(const sk_plan &plan) {
     return f;
 }
 
-cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n, double *out,
+// nvec > 1 (values only): one launch per coefficient vector of the K×nvec block, θ read with stride nvec.  For a
+// handful of vectors this beats the DMMA kernel (sk_block.cu), whose narrowest tile is 8 vectors wide.
+cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out,
                                  cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    if (nvec > 1) {
+        for (int v = 0; v < nvec; v++) {
+            cudaError_t e = smolyak_leaf_lincomb_one(plan, theta + v, nvec, x, n, out + v, nvec, stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    return smolyak_leaf_lincomb_one(plan, theta, 1, x, n, out, plan.E, stream);
+}
+
+static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
+                                            double *out, int64_t out_stride, cudaStream_t stream) {
     const int d = plan.basis.d, LL = leaf_depth(plan), nup = d - LL;
     LeafParams q{};
     q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
+    q.theta_stride = theta_stride; q.out_stride = out_stride;
     q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];

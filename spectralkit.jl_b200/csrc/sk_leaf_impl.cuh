@@ -290,6 +290,7 @@ struct LeafParams {
     const uint32_t *units;        // r | carry << 8
     const uint32_t *thmap;        // shared-memory slot of every coefficient (pair-aligned blocks, see leaf_end)
     int64_t n, K, n_units, Kslots;
+    int64_t theta_stride, out_stride;   // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     int D, nup;
     sk_transform tr[SK_MAX_DIM];
 };
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
     uint32_t *s_units = reinterpret_cast<uint32_t *>(smem_raw + lay.units);
     double *s_theta = reinterpret_cast<double *>(smem_raw + lay.theta);
     for (int64_t i = tid; i < q.n_units; i += NT) s_units[i] = q.units[i];
-    for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i];
+    for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i * q.theta_stride];
     __syncthreads();
 #define UP(u, f) up[((size_t)(u) * NF + (f)) * NT + tid]
     constexpr int NCL = NC<GRAD, LL>::value;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
                 }
             }
         }
-        double *o = q.out + p * E;
+        double *o = q.out + p * q.out_stride;
         if (live) {
             if (NUP > 0) {
                 for (int m = 0; m < E; m++) __stcs(o + m, UP(NUP - 1, F_ACC + m));
