@@ -373,6 +373,24 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         CK(cudaMemcpy(p->d_idx, p->set.idx.data(), p->set.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&p->d_runs, prog.size() * sizeof(uint32_t)));
         CK(cudaMemcpy(p->d_runs, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (p->ncomp == 0 && p->H <= 4096 && d <= 16) {
+            // compact factor lists for the direct kernels: dim << 12 | index-1 of the indices != 1, 0xFFFF-terminated
+            std::vector<uint16_t> fac((size_t)p->K * 8, 0xFFFF);
+            bool ok = true;
+            for (int64_t k = 0; k < p->K && ok; k++) {
+                int nf = 0;
+                for (int j = 0; j < d; j++) {
+                    const int i = p->set.idx[(size_t)k * d + j];
+                    if (i == 1) continue;
+                    if (nf == 8) { ok = false; break; }
+                    fac[(size_t)k * 8 + nf++] = (uint16_t)((j << 12) | (i - 1));
+                }
+            }
+            if (ok) {
+                CK(cudaMalloc(&p->d_fac, fac.size() * sizeof(uint16_t)));
+                CK(cudaMemcpy(p->d_fac, fac.data(), fac.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            }
+        }
         if (p->ncomp == 0) {
             std::vector<uint32_t> bprog;
             if (skk::smolyak_block_program(*p, bprog, &p->bprog_F, &p->bprog_HL)) {
@@ -405,6 +423,7 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_runs) cudaFree(plan->d_runs);
         if (plan->d_units) cudaFree(plan->d_units);
         if (plan->d_thmap) cudaFree(plan->d_thmap);
+        if (plan->d_fac) cudaFree(plan->d_fac);
         for (sk_workspace *w : plan->ws_free) workspace_destroy(w);
         plan->ws_free.clear();
         if (plan->d_bprog) cudaFree(plan->d_bprog);

@@ -80,6 +80,7 @@ struct sk_plan {
     skh::SmolyakSet set;
     // device tables (Smolyak)
     uint16_t *d_idx = nullptr;   // [K][d]
+    uint16_t *d_fac = nullptr;   // [K][8] non-unit factors per term (values-only plans; direct kernels)
     uint32_t *d_runs = nullptr;  // [n_runs] run_len | carry << 24   (generic nested kernel)
     int64_t n_runs = 0;
     uint32_t *d_units = nullptr; // [n_units] r | carry << 8             (unrolled-leaf kernel)

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 #include "sk_device.cuh"
 #include "sk_launch.h"
@@ -251,11 +252,14 @@ struct DirectParams {
     int d, H, ncomp, E;          // ncomp == 0: plain point (E = 1)
     int64_t K, n, ld;
     const uint16_t *idx;
+    const uint4 *fac;            // values-only plans: per term, the factors with index != 1 (8 × uint16: dim << 12 | index-1,
+                                 // 0xFFFF = none), in dimension order; multiplying by T_0 = 1.0 is exact, so it is skipped
     const double *theta;
     int nvec;
     const double *x;
     double *out;
     int64_t k_chunk;             // BASIS: terms per blockIdx.y
+    int no_bulk;                 // BASIS: plain coalesced stores instead of staged bulk copies
     sk_transform tr[SK_MAX_DIM];
     int8_t orders[SK_MAX_COMP][SK_MAX_DIM];
 };
@@ -289,6 +293,28 @@ __device__ __forceinline__ double term_product(const DirectParams &q, const uint
     return b;
 }
 
+// values only: the same left-to-right product over the factors that are not T_0 = 1 (x·1.0 == x bit for bit)
+__device__ __forceinline__ double term_product_compact(const DirectParams &q, int64_t k, const double *tab, int P, int tid) {
+    const uint4 w = __ldg(q.fac + k);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    double b = 1.0;
+    bool first = true;
+#pragma unroll
+    for (int f = 0; f < 8; f++) {
+        const uint32_t e = (ws[f >> 1] >> (16 * (f & 1))) & 0xFFFFu;
+        if (e == 0xFFFFu) break;
+        const double t = tab[((size_t)(e >> 12) * q.H + (e & 0xFFFu)) * P + tid];
+        b = first ? t : b * t;
+        first = false;
+    }
+    return b;
+}
+template <int EMAX>
+__device__ __forceinline__ double term_value(const DirectParams &q, int64_t k, int c, const double *tab, int P, int tid) {
+    if (EMAX == 1 && q.fac) return term_product_compact(q, k, tab, P, tid);
+    return term_product<EMAX>(q, q.idx + (size_t)k * q.d, c, tab, P, tid);
+}
+
 // Block = P points (x) × ny component lanes (y).  The sequential sum s = s + θ_k·b_k of one component of one
 // point is one thread's job (the reference's order), but components — and coefficient vectors — are
 // independent, so they run on different threads: the tables limit a CTA to P = 32..128 points, and this is
@@ -309,7 +335,7 @@ __global__ void smolyak_direct_lincomb_kernel(const __grid_constant__ DirectPara
             for (int c = ty; c < nc; c += ny) {
                 double s = 0.0;
                 for (int64_t k = 0; k < q.K; k++) {
-                    const double b = term_product<EMAX>(q, q.idx + (size_t)k * q.d, c, tab, P, tid);
+                    const double b = term_value<EMAX>(q, k, c, tab, P, tid);
                     const double th = q.theta[k];
                     s = k == 0 ? th * b : s + th * b;      // generic_api.jl:114-128: mul then add, never fused
                 }
@@ -320,7 +346,7 @@ __global__ void smolyak_direct_lincomb_kernel(const __grid_constant__ DirectPara
             for (int v0 = ty * 8; v0 < q.nvec; v0 += ny * 8) {
                 double s[8];
                 for (int64_t k = 0; k < q.K; k++) {
-                    const double b = term_product<EMAX>(q, q.idx + (size_t)k * q.d, 0, tab, P, tid);
+                    const double b = term_value<EMAX>(q, k, 0, tab, P, tid);
                     const double *tk = q.theta + (size_t)k * q.nvec + v0;
 #pragma unroll
                     for (int v = 0; v < 8; v++)
@@ -335,35 +361,41 @@ __global__ void smolyak_direct_lincomb_kernel(const __grid_constant__ DirectPara
     }
 }
 
-// basis_at / collocation: blockIdx.x = tile of P points, blockIdx.y = chunk of terms.
-// Staging is [3][P*E] doubles after the tables.
+// basis_at / collocation: blockIdx.x = tile of P points, blockIdx.y = chunk of terms; block = P points (x) × ny term
+// lanes (y): lane ty produces the terms k0 + ty, k0 + ty + ny, … of its chunk.  (The tables allow 32..128 points per
+// CTA; the term lanes are what fills the SM with warps — output is 8·E bytes per ≈ d multiplies, HBM-write-bound.)
+// Each lane stages its column segment (P·E doubles, contiguous in the column-major result) in its own ring of 3
+// buffers and one elected thread streams it out with the bulk-copy engine; lanes synchronise on their own named
+// barrier.  Partial tiles / unaligned destinations use plain coalesced stores.
 template <int EMAX>
 __global__ void smolyak_direct_basis_kernel(const __grid_constant__ DirectParams q) {
     extern __shared__ double smem[];
-    const int P = blockDim.x, tid = threadIdx.x;
+    const int P = blockDim.x, tid = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
     const int E = q.E;
     double *tab = smem;
-    double *stage = smem + (size_t)q.d * q.H * EMAX * P;
+    double *stage = smem + (size_t)q.d * q.H * EMAX * P + (size_t)ty * 3 * P * E;
     const int64_t p0 = (int64_t)blockIdx.x * P, p = p0 + tid;
     const bool live = p < q.n, full = p0 + P <= q.n;
-    build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid, 0, 1);
+    build_tables<EMAX>(q, q.x + (size_t)(live ? p : 0) * q.d, live, tab, P, tid, ty, ny);
+    __syncthreads();
     const int64_t k0 = (int64_t)blockIdx.y * q.k_chunk, k1 = min(q.K, k0 + q.k_chunk);
     int buf = 0;
-    for (int64_t k = k0; k < k1; k++) {
-        const uint16_t *ik = q.idx + (size_t)k * q.d;
+    for (int64_t k = k0 + ty; k < k1; k += ny) {
         double *g = q.out + ((size_t)k * q.ld + p0) * E;
-        const bool bulk = full && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (((size_t)P * E * 8) % 16 == 0);
+        const bool bulk = !q.no_bulk && full && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (((size_t)P * E * 8) % 16 == 0);
         double *st = stage + (size_t)buf * P * E;
         for (int c = 0; c < E; c++) {
-            double b = term_product<EMAX>(q, ik, c, tab, P, tid);
+            double b = term_value<EMAX>(q, k, c, tab, P, tid);
             if (bulk) st[tid * E + c] = b;
-            else if (live) g[(size_t)tid * E + c] = b;
+            else if (live) __stcs(g + (size_t)tid * E + c, b);
         }
         if (bulk) {
             bulk_store_fence();
-            __syncthreads();
+            asm volatile("bar.sync %0, %1;" ::"r"(ty + 1), "r"(P) : "memory");      // this lane's P threads
             if (tid == 0) { bulk_store(g, st, (uint32_t)(P * E * 8)); bulk_store_wait_read_1(); }
             buf = buf == 2 ? 0 : buf + 1;
+            // the buffer written two terms from now was handed to the copy engine one term ago and its read has
+            // completed (wait_group.read 1) before thread 0 passes the next barrier
         }
     }
     if (tid == 0) bulk_store_wait_all();
@@ -371,7 +403,7 @@ __global__ void smolyak_direct_basis_kernel(const __grid_constant__ DirectParams
 
 static void fill_direct_params(const sk_plan &plan, DirectParams &q) {
     q.d = plan.basis.d; q.H = (int)plan.H; q.ncomp = plan.ncomp; q.E = plan.ncomp ? plan.ncomp : 1;
-    q.K = plan.K; q.idx = plan.d_idx;
+    q.K = plan.K; q.idx = plan.d_idx; q.fac = reinterpret_cast<const uint4 *>(plan.d_fac);
     for (int j = 0; j < q.d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
@@ -432,23 +464,41 @@ cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_
     DirectParams q{};
     fill_direct_params(plan, q);
     q.theta = nullptr; q.nvec = 1; q.x = x; q.out = out; q.n = n; q.ld = ld;
+    // E == 1: a warp's 32 values are already contiguous in the column, plain streaming stores win (1.73 vs 1.53 TB/s);
+    // E > 1: the staged bulk copy makes the interleaved components one contiguous segment (189 vs 174 GB/s).
+    // SK_BASIS_NO_BULK=0/1 forces either (experiments)
+    static const int force = [] { const char *e = getenv("SK_BASIS_NO_BULK"); return e ? atoi(e) : -1; }();
+    q.no_bulk = force >= 0 ? force : (q.E == 1);
     const int emax = plan_emax(plan);
-    size_t per_point = (size_t)q.d * q.H * emax * sizeof(double) + 3 * (size_t)q.E * sizeof(double);
-    int P = pick_points_per_block(per_point, 200 * 1024);
+    const size_t tab_point = (size_t)q.d * q.H * emax * sizeof(double);
+    const size_t limit = 200 * 1024;
+    int P = 0, ny = 1;
+    // points per CTA: P = 64 (two warps per lane) with as many term lanes as fit (<= 8: 15 named barriers, 512+
+    // threads); fall back to fewer points when the tables are large
+    for (int cand : {64, 32, 128}) {
+        for (int lanes = 8; lanes >= 1; lanes >>= 1) {
+            if (cand * lanes > 1024) continue;
+            if ((tab_point + 3 * (size_t)lanes * q.E * sizeof(double)) * cand <= limit) { P = cand; ny = lanes; break; }
+        }
+        if (P) break;
+    }
     if (!P) return cudaErrorInvalidConfiguration;
-    size_t smem = per_point * P;
+    const size_t smem = (tab_point + 3 * (size_t)ny * q.E * sizeof(double)) * P;
     int64_t tiles = (n + P - 1) / P;
     // enough blocks to fill the machine: split the K terms when there are few point tiles
     int64_t want_chunks = std::max<int64_t>(1, ((int64_t)sm_count() * 2 + tiles - 1) / tiles);
-    int64_t chunks = std::min<int64_t>(want_chunks, std::max<int64_t>(1, q.K / 64));
+    int64_t chunks = std::min<int64_t>(want_chunks, std::max<int64_t>(1, q.K / (16 * ny)));
     chunks = std::min<int64_t>(chunks, 65535);
     q.k_chunk = (q.K + chunks - 1) / chunks;
     dim3 grid((unsigned)tiles, (unsigned)((q.K + q.k_chunk - 1) / q.k_chunk));
     cudaError_t e;
 #define SK_LAUNCH_DB(EM)                                                   \
     do {                                                                   \
-        e = set_smem(smolyak_direct_basis_kernel<EM>, smem);               \
-        if (e == cudaSuccess) smolyak_direct_basis_kernel<EM><<<grid, P, smem, stream>>>(q); \
+        cudaFuncAttributes fa;                                             \
+        e = cudaFuncGetAttributes(&fa, smolyak_direct_basis_kernel<EM>);   \
+        if (e == cudaSuccess) while (ny > 1 && (int64_t)fa.numRegs * P * ny > 65536) ny >>= 1;   /* register file */ \
+        if (e == cudaSuccess) e = set_smem(smolyak_direct_basis_kernel<EM>, smem);               \
+        if (e == cudaSuccess) smolyak_direct_basis_kernel<EM><<<grid, dim3(P, ny), smem, stream>>>(q); \
     } while (0)
     if (emax == 1) SK_LAUNCH_DB(1); else if (emax == 2) SK_LAUNCH_DB(2); else if (emax == 3) SK_LAUNCH_DB(3); else SK_LAUNCH_DB(6);
 #undef SK_LAUNCH_DB
