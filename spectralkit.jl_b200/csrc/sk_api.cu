@@ -358,7 +358,10 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         for (int j = 0; j < d; j++) ftab += (double)(p->H - 1) * (p->deg[j] == 0 ? 2 : p->deg[j] == 1 ? 6 : 12);
         p->flops_direct = (double)p->K * (C * (d - 1) + 2 * C) + ftab;
         p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
-        p->flops_fast = p->fast_kernel == 2 ? skk::smolyak_leaf_flops(*p) : p->fast_kernel == 1 ? skk::smolyak_nested_flops(*p) : p->flops_direct;
+        if (!p->fast_kernel && p->fast_mode < 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+        p->n_runs = (int64_t)p->set.run_len.size();
+        p->flops_fast = p->fast_kernel == 2 ? skk::smolyak_leaf_flops(*p) : p->fast_kernel == 1 ? skk::smolyak_nested_flops(*p)
+                        : p->fast_kernel == 3 ? skk::smolyak_general_flops(*p) : p->flops_direct;
     }
     // the reference throws for order >= 2 through the rational maps (transformations.jl:266,332)
     for (int j = 0; j < d; j++)
@@ -398,6 +401,12 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
                 CK(cudaMemcpy(p->d_bprog, bprog.data(), bprog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             }
         }
+        if (p->fast_kernel == 3) {
+            std::vector<uint16_t> tree;
+            if (!skk::smolyak_general_tree(*p, tree, p->tree_lvl)) SK_FAIL(SK_ERR_ARGUMENT, "internal error: prefix tree");
+            CK(cudaMalloc(&p->d_tree, tree.size() * sizeof(uint16_t)));
+            CK(cudaMemcpy(p->d_tree, tree.data(), tree.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        }
         if (p->fast_kernel == 2) {
             std::vector<uint32_t> units;
             skk::smolyak_leaf_units(*p, units);
@@ -424,6 +433,7 @@ int sk_plan_destroy(sk_plan *plan) {
         if (plan->d_units) cudaFree(plan->d_units);
         if (plan->d_thmap) cudaFree(plan->d_thmap);
         if (plan->d_fac) cudaFree(plan->d_fac);
+        if (plan->d_tree) cudaFree(plan->d_tree);
         for (sk_workspace *w : plan->ws_free) workspace_destroy(w);
         plan->ws_free.clear();
         if (plan->d_bprog) cudaFree(plan->d_bprog);
@@ -466,6 +476,10 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
     // a few coefficient vectors: one unrolled-leaf launch per vector beats the 8-wide DMMA tile (values only)
     if (!exact && plan->fast_kernel == 2 && (nvec == 1 || (nvec <= leaf_per_vector_max() && plan->fast_mode == 0))) {
         CK(skk::smolyak_leaf_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    if (!exact && nvec == 1 && plan->fast_kernel == 3) {
+        CK(skk::smolyak_general_lincomb(*plan, d_theta, d_x, n, d_out, stream));
         return SK_OK;
     }
     if (!exact && nvec == 1 && plan->fast_kernel == 1) {

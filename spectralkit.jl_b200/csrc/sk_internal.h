@@ -89,7 +89,9 @@ struct sk_plan {
     int64_t theta_slots = 0;
     uint32_t *d_bprog = nullptr; // factor program of the coefficient-block kernel (sk_block.cu)
     int bprog_F = 0, bprog_HL = 0;
-    int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves
+    uint16_t *d_tree = nullptr;  // prefix tree of the component table (general nested kernel)
+    std::vector<int> tree_lvl;   // first prefix of every level, then the total
+    int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves, 3 general nested (any ∂ spec)
     double flops_fast = 0, flops_direct = 0;
     // host-buffer staging pool (the only mutable state of a plan; guarded by ws_mu)
     mutable std::mutex ws_mu;

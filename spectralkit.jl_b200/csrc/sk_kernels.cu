@@ -447,7 +447,7 @@ cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int
     do {                                                                                 \
         cudaFuncAttributes fa;                                                           \
         e = cudaFuncGetAttributes(&fa, smolyak_direct_lincomb_kernel<EM>);               \
-        if (e == cudaSuccess) ny = std::max(1, std::min(ny, 65536 / std::max(fa.numRegs, 1) / P));   /* register file */ \
+        if (e == cudaSuccess) ny = std::max(1, std::min(ny, fa.maxThreadsPerBlock / P));   /* register file */ \
         if (e == cudaSuccess) e = set_smem(smolyak_direct_lincomb_kernel<EM>, smem);     \
         if (e == cudaSuccess) smolyak_direct_lincomb_kernel<EM><<<grid, dim3(P, ny), smem, stream>>>(q); \
     } while (0)
@@ -496,7 +496,7 @@ cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_
     do {                                                                   \
         cudaFuncAttributes fa;                                             \
         e = cudaFuncGetAttributes(&fa, smolyak_direct_basis_kernel<EM>);   \
-        if (e == cudaSuccess) while (ny > 1 && (int64_t)fa.numRegs * P * ny > 65536) ny >>= 1;   /* register file */ \
+        if (e == cudaSuccess) while (ny > 1 && P * ny > fa.maxThreadsPerBlock) ny >>= 1;   /* register file */ \
         if (e == cudaSuccess) e = set_smem(smolyak_direct_basis_kernel<EM>, smem);               \
         if (e == cudaSuccess) smolyak_direct_basis_kernel<EM><<<grid, dim3(P, ny), smem, stream>>>(q); \
     } while (0)

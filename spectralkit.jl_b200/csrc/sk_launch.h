@@ -34,6 +34,13 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int n
                                  double *out, cudaStream_t stream);
 double smolyak_leaf_flops(const sk_plan &plan);
 
+// ---- Smolyak, nested evaluation for any ∂ specification with per-coordinate orders <= 2 (sk_general.cu)
+bool smolyak_general_supported(const sk_plan &plan);
+bool smolyak_general_tree(const sk_plan &plan, std::vector<uint16_t> &tree, std::vector<int> &lvl_off);
+cudaError_t smolyak_general_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n, double *out,
+                                    cudaStream_t stream);
+double smolyak_general_flops(const sk_plan &plan);
+
 // ---- Smolyak with a K×nvec coefficient block: on-chip collocation tiles × Θ with FP64 DMMA (sk_block.cu)
 bool smolyak_block_supported(const sk_plan &plan);
 bool smolyak_block_program(const sk_plan &plan, std::vector<uint32_t> &prog, int *F, int *HL);

@@ -360,6 +360,54 @@ def test_smolyak_svector_coefficients(orc):
         assert same(got[:, v], sk.linear_combination(basis, theta[:, v].copy(), x, exact=True))
 
 
+# ---- general ∂ specifications through the fast general nested kernel (fast_path 3)
+@pytest.mark.parametrize("code,d,B,parts", [
+    (2, 2, 3, [(1, 1)]),                                  # test/test_smolyak.jl:39: ∂(1, 1) → [f, ∂1, ∂2, ∂1∂2]
+    (0, 3, 3, [(1, 1), (0, 2)]),
+    (1, 4, 3, [(2,), (0, 2), (0, 0, 2), (0, 0, 0, 2)]),   # value + diagonal of the Hessian
+    (2, 6, 4, [(1, 1), (0, 1, 1), (0, 0, 0, 2, 1), (1, 0, 0, 0, 0, 1)]),
+    (2, 3, 4, [(2, 2, 2)]),                               # every order up to 2 in every coordinate: 27 components
+    (2, 1, 4, [(2,)]),
+    (2, 8, 3, [(0, 0, 0, 0, 0, 0, 1, 1), (2,)]),
+])
+def test_smolyak_general_spec_fast(orc, code, d, B, parts):
+    rng = np.random.default_rng(4242 + d + B)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    spec = sk.partial(*parts[0])
+    for q in parts[1:]:
+        spec = spec | sk.partial(*q)
+    ospec = orc.deriv_spec(parts, d)
+    assert sk.get_plan(basis, 0, spec).info.fast_path == 3
+    theta = rng.standard_normal(sk.dimension(basis))
+    x = rand_pm1(rng, (333, d))
+    want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
+    scale = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec, absmode=True)
+    got = sk.linear_combination(basis, theta, spec(x))
+    assert got.shape == want.shape and within(got, want, scale)
+    assert same(sk.linear_combination(basis, theta, spec(x), exact=True), want)
+
+
+def test_smolyak_general_spec_fast_transformed(orc):
+    # mixed transformations; second derivatives through the rational maps are the opt-in extension
+    rng = np.random.default_rng(99)
+    d, B = 4, 3
+    trs = [mk_tr(orc, 1, 0, 4), mk_tr(orc, 2, 1, 2), mk_tr(orc, 3, 0, 4), mk_tr(orc, 1, -1, 2)]
+    ct = sk.coordinate_transformations(*[t[0] for t in trs])
+    otr = [t[1] for t in trs]
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    theta = rng.standard_normal(sk.dimension(basis))
+    y = sk.transform_from(basis, ct, rng.uniform(-0.95, 0.95, (200, d)))
+    for parts, ext in (([(1, 1), (0, 0, 1, 1)], False), ([(2,), (0, 1, 1), (0, 0, 0, 2)], False), ([(1, 2), (0, 0, 2)], True)):
+        spec = sk.partial(*parts[0])
+        for q in parts[1:]:
+            spec = spec | sk.partial(*q)
+        ospec = orc.deriv_spec(parts, d)
+        want = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec, ext2=ext)
+        scale = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec, ext2=ext, absmode=True)
+        got = sk.linear_combination(basis @ ct, theta, spec(y), allow_rational_d2=ext)
+        assert within(got, want, scale)
+
+
 # ---- K4: coefficient block (SVector coefficients) through the DMMA kernel, fast mode
 @pytest.mark.parametrize("code,d,B,nvec,n", [
     (2, 4, 3, 11, 100),      # odd nvec: generic Θ loader, scalar epilogue stores; partial point tile
