@@ -178,6 +178,7 @@ def run_ours(args):
 
     # FP64 denominators (MEASURED_PEAKS.json has no FP64 figure): measured live on this GPU
     dfma_burst, dfma_sust = sk.fp64_peak(local, 0, 0.4)
+    _, dfma3_sust = sk.fp64_peak(local, 3, 0.3)       # DFMA with three distinct register operands: register-file bound
 
     for _ in range(args.warmup):
         step_device()
@@ -269,7 +270,10 @@ def run_ours(args):
                          "traffic": traffic, "kernel": "smolyak_leaf_kernel<InteriorGrid2, LL=6, GRAD> (spectralkit.jl_b200/csrc/sk_leaf_impl.cuh)", "kernel_ms": kernel_ms,
                          "flops_per_point": flops_pt, "flops_per_point_reference_direct": float(info.flops_per_point_direct),
                          "peak_source": "measured live: sk_fp64_peak DFMA sustained (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2 TFLOP/s",
-                         "peak_burst": dfma_burst, "hbm_gbs": hbm_gbs,
+                         "peak_burst": dfma_burst, "peak_three_register_operands": dfma3_sust,
+                         "frac_of_three_register_operand_rate": achieved / dfma3_sust,
+                         "note": "B200's register file cannot feed three fresh 64-bit operands per DFMA at the pipe rate: fma(a,b,c) with three distinct registers runs at peak_three_register_operands, with one reused/uniform operand at ~0.97 of peak (profiles/micro/dfma_operands.cu); 16 % of this kernel's DFMAs carry .reuse",
+                         "hbm_gbs": hbm_gbs,
                          "hbm_frac_of_measured": hbm_gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None},
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": e2e_n * D * 8 + K * 8, "d2h_bytes_per_step": e2e_n * (D + 1) * 8,
                     "points_per_gpu": e2e_n, "ms_per_step": e2e_ms},

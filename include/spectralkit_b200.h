@@ -197,7 +197,8 @@ int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double 
 
 /* ---------------------------------------------------------------- measurement helpers */
 /* Measures the FP64 pipe on `device`: which = 0 DFMA (CUDA-core), 1 DMMA (mma.sync m8n8k4 f64),
- * 2 both at once (half the warps each: shows whether they share one pipe).
+ * 2 both at once (half the warps each: shows whether they share one pipe), 3 DFMA with three distinct register
+ * operands per instruction (the register-file-bound rate of code without operand reuse).
  * Runs for about `seconds`; returns TFLOP/s of the best (burst) and of the whole loop (sustained). */
 int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained);
 /* Number of kernel launches issued by this library since load (all threads). */

@@ -765,7 +765,8 @@ def transform_from(dom_or_basis, t, x, *, device: int = 0):
 
 
 def fp64_peak(device: int = 0, which: int = 0, seconds: float = 0.5):
-    """(burst, sustained) TFLOP/s of the FP64 pipe: which = 0 DFMA, 1 DMMA."""
+    """(burst, sustained) TFLOP/s of the FP64 pipe: which = 0 DFMA, 1 DMMA, 2 both at once, 3 DFMA with three
+    distinct register operands (register-file bound)."""
     b, s = C.c_double(0), C.c_double(0)
     L.check(L.lib.sk_fp64_peak(device, which, seconds, C.byref(b), C.byref(s)))
     return b.value, s.value

@@ -729,7 +729,7 @@ int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double 
 
 // ------------------------------------------------------------------------------ measurement
 int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained) {
-    if (which < 0 || which > 2 || !tflops_burst || !tflops_sustained) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
+    if (which < 0 || which > 3 || !tflops_burst || !tflops_sustained) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
     int ndev = 0;
     int rc = sk_device_count(&ndev);
     if (rc != SK_OK) return rc;

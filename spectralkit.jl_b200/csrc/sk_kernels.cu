@@ -596,6 +596,26 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// which == 3: DFMA with THREE distinct register operands per instruction (a[i] = fma(a[i], b[i], c[i])).  The peak
+// kernel above has two loop-invariant operands (operand-reuse cache); real evaluation code mostly does not, and the
+// register file cannot deliver three fresh 64-bit operands at the pipe's issue rate: 20.6 vs 36 TFLOP/s on B200
+// (profiles/micro/dfma_operands.cu).  Reported next to the peak as the practical ceiling of such code.
+__global__ void __launch_bounds__(256) dfma3_peak_kernel(int iters, double *sink) {
+    double a[16], b[16], c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { a[i] = 1.0 + i * 1e-3 + threadIdx.x * 1e-6; b[i] = 1.0 - (i + threadIdx.x) * 1e-9; c[i] = 1e-9 * (i + 1 + threadIdx.x); }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = fma(a[i], b[i], c[i]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = __longlong_as_double(__double_as_longlong(b[i]) ^ (long long)(it & 1));   // keeps b live, no FP64 work
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i] + b[i] + c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
 // which == 2: even warps run the DFMA chains, odd warps the DMMA tiles — do the two share one pipe?
 __global__ void __launch_bounds__(256) dmix_peak_kernel(int iters, double *sink) {
     double s = 0;
@@ -629,7 +649,10 @@ __global__ void __launch_bounds__(256) dmix_peak_kernel(int iters, double *sink)
 
 cudaError_t fp64_peak_launch(int which, int iters, double *sink, double *flops, cudaStream_t stream) {
     int blocks = sm_count() * 8, threads = 256;
-    if (which == 2) {
+    if (which == 3) {
+        dfma3_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+        *flops = 2.0 * 16 * (double)iters * blocks * threads;
+    } else if (which == 2) {
         dmix_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
         *flops = (2.0 * 16 * 32 + 2.0 * 8 * 8 * 4 * 8) * (double)iters * blocks * (threads / 64);
     } else if (which == 0) {
