@@ -184,6 +184,24 @@ function collocation_solve_gpu(basis, y::Vector{SVector{M,Float64}}) where {M}
     θ
 end
 
+# ---- refinement between bases (chebyshev.jl:133-142, smolyak_api.jl:141-208, generic_api.jl:314-322) ----
+function is_subset_basis_library(basis1, basis2)
+    p1, t1 = split(basis1); p2, t2 = split(basis2)
+    out = Ref{Cint}(0)
+    check(ccall((:sk_is_subset_basis, libsk), Cint,
+                (Ref{SkBasisDesc}, Ptr{SkTransform}, Ref{SkBasisDesc}, Ptr{SkTransform}, Ref{Cint}),
+                desc(p1), t1 === nothing ? C_NULL : t1, desc(p2), t2 === nothing ? C_NULL : t2, out))
+    out[] != 0
+end
+function augment_coefficients_library(basis1, basis2, θ1::Vector{Float64})
+    p1, t1 = split(basis1); p2, t2 = split(basis2)
+    θ2 = Vector{Float64}(undef, dimension(basis2))
+    GC.@preserve θ1 θ2 check(ccall((:sk_augment_coefficients, libsk), Cint,
+        (Ref{SkBasisDesc}, Ptr{SkTransform}, Ref{SkBasisDesc}, Ptr{SkTransform}, Ptr{Float64}, Int64, Cint, Ptr{Float64}),
+        desc(p1), t1 === nothing ? C_NULL : t1, desc(p2), t2 === nothing ? C_NULL : t2, θ1, length(θ1), 1, θ2))
+    θ2
+end
+
 # ---- metadata that must be bit-exact (SURVEY.md §8(b)) -------------------------------------------
 "collect(grid(basis)) computed by the library (correctly rounded sinpi/cospi); compare with `collect(grid(basis))`."
 function grid_gpu_library(basis)

@@ -519,6 +519,39 @@ def test_augmented_coefficients_evaluate_equally(orc):
     np.testing.assert_allclose(sk.linear_combination(c2, sk.augment_coefficients(c1, c2, th), y), sk.linear_combination(c1, th, y), rtol=1e-13, atol=1e-13)
 
 
+def test_edge_cases_empty_single_and_degenerate(orc):
+    import torch
+    rng = np.random.default_rng(5)
+    b6 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), 6)
+    K = sk.dimension(b6)
+    th = rng.standard_normal(K)
+    # empty batches (host and device) for every entry point of the path
+    assert sk.linear_combination(b6, th, np.empty((0, 6))).shape == (0,)
+    assert sk.linear_combination(b6, th, sk.gradient(6)(np.empty((0, 6)))).shape == (0, 7)
+    assert sk.linear_combination(b6, rng.standard_normal((K, 3)), np.empty((0, 6))).shape == (0, 3)
+    assert sk.linear_combination(b6, torch.as_tensor(th).cuda(), torch.empty((0, 6), dtype=torch.float64, device="cuda")).shape == (0,)
+    assert sk.basis_at(b6, np.empty((0, 6))).shape[:2] == (0, K)
+    c20 = sk.Chebyshev(sk.InteriorGrid(), 20)
+    assert sk.linear_combination(c20, np.ones(20), np.empty(0)).shape == (0,)
+    # a single point drops the leading axis, like the reference's pointwise call
+    x1 = rng.uniform(-1, 1, 6)
+    v = sk.linear_combination(b6, th, x1)
+    assert np.ndim(v) == 0 and abs(v - orc.smolyak_lincomb(2, 6, 4, 4, th, x1[None, :])[0, 0]) <= 1e-13 * orc.smolyak_lincomb(2, 6, 4, 4, th, x1[None, :], absmode=True)[0, 0]
+    # degenerate bases: B = 0 (one basis function), through the leaf, block and exact kernels
+    b0 = sk.smolyak_basis(sk.Chebyshev, sk.EndpointGrid(), sk.SmolyakParameters(0), 3)
+    assert sk.dimension(b0) == 1
+    x = rand_pm1(rng, (70, 3))
+    assert same(sk.linear_combination(b0, np.array([2.5]), x), np.full(70, 2.5))
+    assert same(sk.linear_combination(b0, np.array([[2.5, -1.0, 3.0]]), x), np.tile([2.5, -1.0, 3.0], (70, 1)))
+    th40 = rng.standard_normal((1, 40))
+    assert same(sk.linear_combination(b0, th40, x), np.tile(th40, (70, 1)))
+    g = sk.linear_combination(b0, np.array([2.5]), sk.gradient(3)(x))
+    assert same(g, np.tile([2.5, 0, 0, 0], (70, 1)))
+    # N = 1 Chebyshev
+    c1 = sk.Chebyshev(sk.EndpointGrid(), 1)
+    assert same(sk.linear_combination(c1, np.array([3.0]), sk.d(np.linspace(-1, 1, 5))), np.tile([3.0, 0.0], (5, 1)))
+
+
 def test_golden_fixtures(orc):
     g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
     b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
