@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <cstdlib>
 
 #include "sk_device.cuh"
@@ -53,13 +54,19 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 // -------------------------------------------------------------------------------------------
 // K1: univariate linear combination, one point per thread, θ staged in shared memory
 // -------------------------------------------------------------------------------------------
-template <int DP1, bool EXACT>
+// θ of the fast kernels in the constant bank: θ is warp-uniform, and a uniform operand (LDCU.64 UR, c[3][UR+imm] →
+// DFMA R, R, UR, R) leaves two register operands per fma — three fresh ones run at 57 % of the DFMA rate
+// (profiles/micro/dfma_operands.cu).  Two slots, reused in stream order (events), so two streams can be in flight.
+constexpr int kUniConstMax = 3840;
+static __constant__ double c_uni_theta[2 * kUniConstMax];
+
+template <int DP1, bool EXACT, bool THC = false>
 __global__ void __launch_bounds__(256) uni_lincomb_kernel(int N, sk_transform tr, const double *__restrict__ theta,
                                                           int theta_in_smem, const double *__restrict__ x, int64_t n,
                                                           double *__restrict__ out) {
     extern __shared__ double s_theta[];
     const double *th = theta;
-    if (theta_in_smem) {
+    if (!THC && theta_in_smem) {
         for (int i = threadIdx.x; i < N; i += blockDim.x) s_theta[i] = theta[i];
         __syncthreads();
         th = s_theta;
@@ -92,7 +99,8 @@ __global__ void __launch_bounds__(256) uni_lincomb_kernel(int N, sk_transform tr
             double fp[DP1], fpp[DP1];
 #pragma unroll
             for (int r = 0; r < DP1; r++) { fp[r] = r == 0 ? 1.0 : 0.0; fpp[r] = xj[r]; }
-            double th0 = th[0];
+            const int cs = theta_in_smem;                              // THC: first constant-bank slot of θ
+            double th0 = THC ? c_uni_theta[cs] : th[0];
 #pragma unroll
             for (int r = 0; r < DP1; r++) s[r] = r == 0 ? th0 : 0.0;
 #pragma unroll 4
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(256) uni_lincomb_kernel(int N, sk_transform tr
                 if (DP1 > 2)
                     f[DP1 > 2 ? 2 : 0] = fma(t0, fp[DP1 > 2 ? 2 : 0],
                                              fma(tt1, fp[DP1 > 1 ? 1 : 0], fma(t2, fp[0], -fpp[DP1 > 2 ? 2 : 0])));
-                double tk = th[k];
+                const double tk = THC ? c_uni_theta[cs + k] : th[k];
 #pragma unroll
                 for (int r = 0; r < DP1; r++) { s[r] = fma(tk, f[r], s[r]); fpp[r] = fp[r]; fp[r] = f[r]; }
             }
@@ -150,6 +158,27 @@ static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const d
     size_t smem = (size_t)N * sizeof(double);
     int in_smem = smem <= 48 * 1024;
     if (!in_smem) smem = 0;
+    static const int use_const = [] { const char *e = getenv("SK_THETA_CONST"); return e ? atoi(e) : 1; }();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!exact && use_const && N <= kUniConstMax && dev < 64) {
+        static std::mutex mu;
+        static cudaEvent_t done[64][2] = {};
+        static unsigned next[64] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        const int slot = (int)(next[dev]++ & 1u);
+        cudaError_t e = cudaSuccess;
+        if (!done[dev][slot]) e = cudaEventCreateWithFlags(&done[dev][slot], cudaEventDisableTiming);
+        else e = cudaStreamWaitEvent(stream, done[dev][slot], 0);       // the launch that last read this slot
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyToSymbolAsync(c_uni_theta, theta, (size_t)N * sizeof(double), (size_t)slot * kUniConstMax * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) return e;
+        uni_lincomb_kernel<(DP1 <= 3 ? DP1 : 1), false, true><<<grid, threads, 0, stream>>>(N, tr, theta, slot * kUniConstMax, x, n, out);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(done[dev][slot], stream);
+    }
     if (exact) uni_lincomb_kernel<DP1, true><<<grid, threads, smem, stream>>>(N, tr, theta, in_smem, x, n, out);
     else uni_lincomb_kernel<(DP1 <= 3 ? DP1 : 1), false><<<grid, threads, smem, stream>>>(N, tr, theta, in_smem, x, n, out);
     count_launch();
