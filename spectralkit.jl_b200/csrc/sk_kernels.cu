@@ -161,7 +161,8 @@ static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const d
     static const int use_const = [] { const char *e = getenv("SK_THETA_CONST"); return e ? atoi(e) : 1; }();
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!exact && use_const && N <= kUniConstMax && dev < 64) {
+    // (small batches stay on the shared-memory path: the symbol copy and the slot event cost ≈ 10 µs of launch latency)
+    if (!exact && use_const && N <= kUniConstMax && dev < 64 && n >= ((int64_t)1 << 17)) {
         static std::mutex mu;
         static cudaEvent_t done[64][2] = {};
         static unsigned next[64] = {};
