@@ -552,6 +552,60 @@ def test_edge_cases_empty_single_and_degenerate(orc):
     assert same(sk.linear_combination(c1, np.array([3.0]), sk.d(np.linspace(-1, 1, 5))), np.tile([3.0, 0.0], (5, 1)))
 
 
+def test_no_out_of_bounds_writes_around_caller_buffers(orc):
+    """compute-sanitizer is not available on the GPU pool: the kernels write into the middle of a sentinel-filled
+    device buffer through the raw C ABI, and everything around the result region must stay untouched.  Ragged sizes
+    (partial tiles in points, vectors and terms) for every kernel family."""
+    import ctypes as C
+    import torch
+    L = sk._lib
+    rng = np.random.default_rng(31)
+    SENT = -7.25e300
+    PAD = 4099                                           # doubles of guard band on each side (odd: misaligns by 8 bytes)
+
+    def run(basis, spec, theta, x, E, exact=False, basis_at=False):
+        plan = sk.get_plan(basis, 0 if not isinstance(spec, int) else spec, None if isinstance(spec, int) else spec, 0)
+        n = x.shape[0]
+        K = plan.info.K
+        words = n * K * E if basis_at else n * E
+        buf = torch.full((words + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        xd = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+        out_ptr = C.c_void_p(buf.data_ptr() + PAD * 8)
+        if basis_at:
+            L.check(L.lib.sk_basis_at(plan.handle, C.c_void_p(xd.data_ptr()), n, out_ptr, n, L.SK_MEM_DEVICE, None))
+        else:
+            th = torch.as_tensor(np.ascontiguousarray(theta)).cuda()
+            nvec = 1 if theta.ndim == 1 else theta.shape[1]
+            flags = L.SK_MEM_DEVICE | (L.SK_MODE_EXACT if exact else L.SK_MODE_FAST)
+            L.check(L.lib.sk_linear_combination(plan.handle, C.c_void_p(th.data_ptr()), K, nvec, C.c_void_p(xd.data_ptr()), n, out_ptr, flags, None))
+        torch.cuda.synchronize()
+        h = buf.cpu().numpy()
+        assert (h[:PAD] == SENT).all() and (h[PAD + words:] == SENT).all(), "write outside the result buffer"
+        assert not (h[PAD:PAD + words] == SENT).any(), "result element never written"
+
+    b6 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), 6)
+    K6 = sk.dimension(b6)
+    b8 = sk.smolyak_basis(sk.Chebyshev, sk.EndpointGrid(), sk.SmolyakParameters(3), 8)
+    K8 = sk.dimension(b8)
+    for n in (1, 383, 385, 1000):
+        x6 = rand_pm1(rng, (n, 6))
+        run(b6, sk.gradient(6), rng.standard_normal(K6), x6, 7)                      # leaf kernel, gradient
+        run(b6, None, rng.standard_normal(K6), x6, 1)                                # leaf kernel, values
+        run(b6, None, rng.standard_normal((K6, 5)), x6, 5)                           # leaf kernel per vector (strided θ / out)
+        run(b6, None, rng.standard_normal((K6, 37)), x6, 37)                         # block kernel, 64-wide tile, odd nvec
+        run(b6, None, rng.standard_normal((K6, 130)), x6, 130)                       # block kernel, 256-wide tile, partial
+        run(b6, sk.partial(1, 1) | sk.partial(0, 0, 2), rng.standard_normal(K6), x6, 6)   # general nested kernel
+        run(b6, sk.gradient(6), rng.standard_normal(K6), x6, 7, exact=True)          # direct kernel, component lanes
+        run(b8, sk.gradient(8), rng.standard_normal(K8), rand_pm1(rng, (n, 8)), 9)   # leaf kernel with the unit interpreter
+    for n in (1, 63, 65, 200):
+        run(b6, None, None, rand_pm1(rng, (n, 6)), 1, basis_at=True)                 # basis_at, values (streaming stores)
+        run(b6, sk.gradient(6), None, rand_pm1(rng, (n, 6)), 7, basis_at=True)       # basis_at, staged bulk copies
+    c = sk.Chebyshev(sk.InteriorGrid(), 33) @ sk.BoundedLinear(-2, 3)
+    for n in (1, 255, 257, 1 << 17):
+        run(c, 1, rng.standard_normal(33), rng.uniform(-2, 3, n), 2)                 # univariate (constant-bank θ above 2^17)
+        run(c, 0, rng.standard_normal((33, 3)), rng.uniform(-2, 3, n), 3)
+
+
 def test_golden_fixtures(orc):
     g = np.load(os.path.join(ge.ROOT, "tests", "golden", "lincomb.npz"))
     b20 = sk.Chebyshev(sk.InteriorGrid(), 20)
