@@ -626,6 +626,25 @@ def test_golden_fixtures(orc):
     assert same(sk.linear_combination(b4, g["c5_theta"], g["c5_y"], exact=True), g["c5_out"])
 
 
+def test_golden_fixtures_extras(orc):
+    # committed vectors for the later paths (tests/golden/make_golden_extras.py): coefficient block, general ∂
+    # specification, refinement, fit
+    g = np.load(os.path.join(ge.ROOT, "tests", "golden", "extras.npz"))
+    ct = sk.coordinate_transformations(sk.BoundedLinear(0, 4), sk.SemiInfRational(1, 2), sk.InfRational(0, 4), sk.BoundedLinear(-1, 2), sk.SemiInfRational(-3, 3))
+    b5 = sk.smolyak_basis(sk.Chebyshev, sk.EndpointGrid(), sk.SmolyakParameters(3), 5) @ ct
+    assert same(sk.linear_combination(b5, g["k4_theta"], g["k4_y"], exact=True), g["k4_out"])
+    assert within(sk.linear_combination(b5, g["k4_theta"], g["k4_y"]), g["k4_out"], g["k4_scale"])                 # block kernel
+    assert within(sk.linear_combination(b5, np.ascontiguousarray(g["k4_theta"][:, :6]), g["k4_y"]), g["k4_out"][:, :6], g["k4_scale"][:, :6])   # leaf per vector
+    ct3 = sk.coordinate_transformations(sk.BoundedLinear(0, 4), sk.SemiInfRational(1, 2), sk.BoundedLinear(-2, 2))
+    b3 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(3), 3) @ ct3
+    spec = sk.partial(1, 1) | sk.partial(0, 0, 2) | sk.partial(2)
+    assert same(sk.linear_combination(b3, g["gs_theta"], spec(g["gs_y"]), exact=True), g["gs_out"])
+    assert within(sk.linear_combination(b3, g["gs_theta"], spec(g["gs_y"])), g["gs_out"], g["gs_scale"])            # general nested kernel
+    bs = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 3)
+    th = sk.collocation_solve(bs, g["cs_y"])
+    assert np.max(np.abs(th - g["cs_theta"])) <= 50 * float(g["cs_cond"]) * np.finfo(float).eps * np.max(np.abs(g["cs_theta"]))
+
+
 def test_device_pointers_and_sharded_driver(orc):
     import torch
     rng = np.random.default_rng(55)

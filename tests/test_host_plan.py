@@ -251,3 +251,10 @@ def test_augment_coefficients_matches_padding_iterator(code, d, p1, p2):
         assert (gv[:, v] == np.array(po.augment_coefficients(code, d, p1[0], p1[1], p2[0], p2[1], list(thv[:, v])))).all()
     c = sk.augment_coefficients(sk.Chebyshev(grid, 4), sk.Chebyshev(grid, 9), np.arange(4.0))
     assert (c == np.array([0, 1, 2, 3, 0, 0, 0, 0, 0.0])).all()
+
+
+def test_augment_coefficients_golden():
+    g = np.load(os.path.join(ge.ROOT, "tests", "golden", "extras.npz"))
+    b1 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(2, 1), 3)
+    b2 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4, 3), 3)
+    assert (sk.augment_coefficients(b1, b2, g["ag_theta1"]) == g["ag_theta2"]).all()
