@@ -201,6 +201,9 @@ int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double 
  * operands per instruction (the register-file-bound rate of code without operand reuse).
  * Runs for about `seconds`; returns TFLOP/s of the best (burst) and of the whole loop (sustained). */
 int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained);
+/* Closed-form FP64 flop count per point of linear_combination with a K×nvec coefficient block (the DMMA kernel:
+ * 2·K·nvec in the contraction + the generation of the collocation tile); nvec == 1: flops_per_point_fast. */
+double sk_coefficient_block_flops(const sk_plan *plan, int nvec);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sk_launch_count(void);
 

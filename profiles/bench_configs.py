@@ -83,7 +83,7 @@ th5 = torch.randn((K5, nv), generator=gen, device="cuda", dtype=torch.float64)
 n5 = 148 * 64 * 16
 x5 = torch.rand((n5, 10), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1
 ms = timed(lambda: sk.linear_combination(b5, th5, x5), reps=2, warm=1)
-f5 = 2.0 * K5 * nv + 4.0 * K5
+f5 = sk._lib.lib.sk_coefficient_block_flops(sk.get_plan(b5).handle, nv)
 print(json.dumps({"config": "cfg5 Smolyak d=10 B=5 x (K x 256) coefficient block, values (K4, DMMA)", "mode": "fast", "points": n5, "ms": ms,
                   "Mpoints_per_s": n5 / ms / 1e3, "flops_per_point": f5, "tflops": n5 * f5 / ms / 1e9,
                   "frac_of_measured_dmma": n5 * f5 / ms / 1e9 / dmma_sust, "seconds_for_1.25e6_points_per_gpu": 1.25e6 / (n5 / ms * 1e3),

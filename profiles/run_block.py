@@ -16,7 +16,7 @@ K = sk.dimension(basis)
 gen = torch.Generator(device="cuda").manual_seed(105)
 theta = torch.randn((K, nvec), generator=gen, device="cuda", dtype=torch.float64)
 x = torch.rand((n, d), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1
-flops = 2.0 * K * nvec + 3.0 * K + 12.0 * d
+flops = sk._lib.lib.sk_coefficient_block_flops(sk.get_plan(basis).handle, nvec)      # closed form of the kernel: 2·K·nvec + (F−1)·K + tables
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(reps):

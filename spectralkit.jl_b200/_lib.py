@@ -58,7 +58,7 @@ EXPORTS = ["sk_version", "sk_last_error", "sk_device_count", "sk_transform_make"
            "sk_nesting_block_length", "sk_grid_shuffle", "sk_dimension", "sk_parent_dimension", "sk_smolyak_indices",
            "sk_grid", "sk_partials_canonical", "sk_plan_create", "sk_plan_destroy", "sk_plan_get_info",
            "sk_linear_combination", "sk_basis_at", "sk_transform_to", "sk_transform_from",
-           "sk_linear_combination_sharded", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_fp64_peak", "sk_launch_count"]
+           "sk_linear_combination_sharded", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_fp64_peak", "sk_launch_count"]
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
@@ -88,6 +88,8 @@ lib.sk_transform_from.argtypes = [C.POINTER(Transform), C.c_int, _vp, C.c_int64,
 lib.sk_linear_combination_sharded.argtypes = [C.POINTER(_vp), C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int64, _vp, C.c_uint32]
 lib.sk_is_subset_basis.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(C.c_int)]
 lib.sk_augment_coefficients.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), _vp, C.c_int64, C.c_int, _vp]
+lib.sk_coefficient_block_flops.argtypes = [_vp, C.c_int]
+lib.sk_coefficient_block_flops.restype = C.c_double
 lib.sk_collocation_solve.argtypes = [_vp, _vp, C.c_int, _vp, C.c_uint32, _vp]
 lib.sk_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp]
 lib.sk_launch_count.restype = C.c_int64

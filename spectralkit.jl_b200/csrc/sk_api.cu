@@ -442,6 +442,12 @@ int sk_plan_destroy(sk_plan *plan) {
     return SK_OK;
 }
 
+double sk_coefficient_block_flops(const sk_plan *plan, int nvec) {
+    if (!plan || nvec < 1) return 0.0;
+    if (plan->basis.kind == SK_BASIS_SMOLYAK && nvec > 1 && skk::smolyak_block_supported(*plan)) return skk::smolyak_block_flops(*plan, nvec);
+    return plan->flops_fast * nvec;
+}
+
 int sk_plan_get_info(const sk_plan *plan, sk_plan_info *info) {
     if (!plan || !info) SK_FAIL(SK_ERR_ARGUMENT, "NULL argument");
     std::memset(info, 0, sizeof *info);

@@ -9,8 +9,10 @@
 //                                 chebyshev.jl:60-70, transformations.jl:183-333)
 //   K3  uni_basis_kernel /        collocation_matrix rows (generic_api.jl:217-227), streamed out
 //       smolyak_direct_kernel<BASIS>  with the bulk-copy engine (cp.async.bulk smem→global)
-//   K2' smolyak_direct_kernel     direct-form Smolyak product + sequential dot in the reference's
+//   K2' smolyak_direct_*_kernel   direct-form Smolyak product + sequential dot in the reference's
 //                                 order (smolyak_traversal.jl:373-379, derivatives.jl:491,502-511)
+// Elsewhere: K2 unrolled-leaf nested kernel (sk_leaf*.cu, headline), generic nested kernel (sk_nested.cu), nested
+// kernel for any ∂ specification (sk_general.cu), K4 coefficient-block DMMA kernel (sk_block.cu), fit (sk_solve.cu).
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
