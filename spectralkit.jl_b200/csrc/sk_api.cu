@@ -359,6 +359,10 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         p->flops_direct = (double)p->K * (C * (d - 1) + 2 * C) + ftab;
         p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
         if (!p->fast_kernel && p->fast_mode < 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+        {   // experiments: SK_FORCE_GENERAL=1 sends every ∂ request the general kernel can serve to it
+            static const int force = [] { const char *e = getenv("SK_FORCE_GENERAL"); return e ? atoi(e) : 0; }();
+            if (force && p->ncomp > 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+        }
         p->n_runs = (int64_t)p->set.run_len.size();
         p->flops_fast = p->fast_kernel == 2 ? skk::smolyak_leaf_flops(*p) : p->fast_kernel == 1 ? skk::smolyak_nested_flops(*p)
                         : p->fast_kernel == 3 ? skk::smolyak_general_flops(*p) : p->flops_direct;
@@ -415,6 +419,7 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
             CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             std::vector<uint32_t> thmap;
             p->theta_slots = skk::smolyak_leaf_theta_map(*p, &thmap);
+            p->leaf_cta = skk::smolyak_leaf_cta(*p);
             if ((int64_t)thmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
             CK(cudaMalloc(&p->d_thmap, thmap.size() * sizeof(uint32_t)));
             CK(cudaMemcpy(p->d_thmap, thmap.data(), thmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -28,6 +28,7 @@ double smolyak_nested_flops(const sk_plan &plan);
 
 // ---- Smolyak, nested evaluation with compile-time unrolled leaves (sk_leaf.cu): the headline kernel
 bool smolyak_leaf_supported(const sk_plan &plan);
+int smolyak_leaf_cta(const sk_plan &plan);
 void smolyak_leaf_units(const sk_plan &plan, std::vector<uint32_t> &units);
 int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);
 cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,

@@ -85,9 +85,23 @@ bool smolyak_leaf_supported(const sk_plan &plan) {
     int64_t n_units = 1;
     if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
     if (n_units * 2 + plan.K > 64 * 1024) return false;        // cannot fit anyway (and keeps the map cheap)
+    return smolyak_leaf_cta(plan) != 0;
+}
+
+// which CTA shape serves the plan: 1 = the tuned full-size CTA, 2 = the 128-thread variant (bases with upper
+// dimensions whose state does not fit otherwise), 0 = neither (θ or the state too large for shared memory)
+int smolyak_leaf_cta(const sk_plan &plan) {
+    const int LL = leaf_depth(plan);
+    const int d = plan.basis.d, nup = d - LL;
+    int64_t n_units = 1;
+    if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
     const bool g = plan.fast_mode == 1;
-    const LeafSmem lay(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, smolyak_leaf_theta_map(plan, nullptr));
-    return lay.total <= 200 * 1024;                              // θ must fit in shared memory next to the rest
+    const int64_t slots = smolyak_leaf_theta_map(plan, nullptr);
+    const size_t limit = 200 * 1024;
+    if (LeafSmem(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, slots).total <= limit) return 1;
+    if (nup > 0 && (LL == 2 || LL == 4 || LL == 6) &&
+        LeafSmem(kLeafSmallNT, LL, leaf_treg_small_c(LL, g), d, nup, n_units, slots).total <= limit) return 2;
+    return 0;
 }
 
 // units: distinct tails (i_{LL+1}..i_d) in traversal order; word = r | carry << 8
@@ -180,7 +194,7 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
     const int d = plan.basis.d, LL = leaf_depth(plan), nup = d - LL;
     LeafParams q{};
     q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
-    q.theta_stride = theta_stride; q.out_stride = out_stride;
+    q.theta_stride = theta_stride; q.out_stride = out_stride; q.small_cta = plan.leaf_cta == 2;
     q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];

@@ -290,6 +290,7 @@ struct LeafParams {
     const uint32_t *units;        // r | carry << 8
     const uint32_t *thmap;        // shared-memory slot of every coefficient (pair-aligned blocks, see leaf_end)
     int64_t n, K, n_units, Kslots;
+    int small_cta;                // use the 128-thread variant (chosen by the plan: shared-memory fit)
     int64_t theta_stride, out_stride;   // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     int D, nup;
     sk_transform tr[SK_MAX_DIM];
@@ -475,6 +476,11 @@ __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
 constexpr int leaf_treg_c(int LL, bool grad) { const int t = grad ? (LL >= 5 ? 2 : 3) : (LL >= 5 ? 3 : 4); return LL < t ? LL : t; }
 constexpr int leaf_minb_c(int LL, bool grad) { return (LL >= 5 || (grad && LL >= 3)) ? 1 : 2; }
 constexpr int leaf_nt_c(int LL, bool grad) { return LL >= 5 ? (grad ? 384 : 512) : 256; }   // threads per CTA
+// small-CTA variants for bases with dimensions above the leaf (d > LL): the upper-level state is (9 + d) doubles per
+// thread and level, which does not fit next to the tables of a 256..512-thread CTA.  128 threads have 255 registers
+// each, so one more dimension's table moves to registers.
+constexpr int kLeafSmallNT = 128;
+constexpr int leaf_treg_small_c(int LL, bool grad) { const int t = grad ? 3 : 4; return LL < t ? LL : t; }
 constexpr int leaf_sync_c(int) { return 0; }       // CTA re-convergence granularity (terms); measured: no gain
 constexpr int leaf_loopd_c(int LL, bool grad) { return grad && LL >= 5 ? LL : 99; }   // first dimension walked by per-block runtime loops
 
@@ -493,6 +499,14 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
         }
     }
 #endif
+    if (q.small_cta) {      // LL in {2, 4, 6} are the depths that occur together with upper dimensions (leaf_rmax_c)
+        switch (LL) {
+        case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_small_c(2, GRAD), 1, 0, leaf_loopd_c(2, GRAD), kLeafSmallNT>(q, stream);
+        case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_small_c(4, GRAD), 1, 0, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
+        case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_small_c(6, GRAD), 1, 0, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (LL) {
     case 1: return launch_leaf<GK, 1, leaf_rmax_c(GK, 1), GRAD, leaf_treg_c(1, GRAD), leaf_minb_c(1, GRAD), leaf_sync_c(1), leaf_loopd_c(1, GRAD), leaf_nt_c(1, GRAD)>(q, stream);
     case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_c(2, GRAD), leaf_minb_c(2, GRAD), leaf_sync_c(2), leaf_loopd_c(2, GRAD), leaf_nt_c(2, GRAD)>(q, stream);
