@@ -89,7 +89,7 @@ bool smolyak_leaf_supported(const sk_plan &plan) {
 }
 
 // which CTA shape serves the plan: 1 = the tuned full-size CTA, 2 = the 128-thread variant (bases with upper
-// dimensions whose state does not fit otherwise), 0 = neither (θ or the state too large for shared memory)
+// dimensions whose state does not fit otherwise), 3 = the same with four register tables, 0 = neither (θ or the state too large for shared memory)
 int smolyak_leaf_cta(const sk_plan &plan) {
     const int LL = leaf_depth(plan);
     const int d = plan.basis.d, nup = d - LL;
@@ -98,9 +98,18 @@ int smolyak_leaf_cta(const sk_plan &plan) {
     const bool g = plan.fast_mode == 1;
     const int64_t slots = smolyak_leaf_theta_map(plan, nullptr);
     const size_t limit = 200 * 1024;
-    if (LeafSmem(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, slots).total <= limit) return 1;
-    if (nup > 0 && (LL == 2 || LL == 4 || LL == 6) &&
-        LeafSmem(kLeafSmallNT, LL, leaf_treg_small_c(LL, g), d, nup, n_units, slots).total <= limit) return 2;
+    if (LeafSmem(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, slots, g).total <= limit) return 1;
+    if (nup > 0 && (LL == 2 || LL == 4 || LL == 6)) {
+        const size_t sm_smem = 227 * 1024;
+        const size_t a = LeafSmem(kLeafSmallNT, LL, leaf_treg_small_c(LL, g), d, nup, n_units, slots, g).total;
+        const size_t b = LeafSmem(kLeafSmallNT, LL, leaf_treg_small_c(LL, g, true), d, nup, n_units, slots, g).total;
+        // gradient with LL >= 4: a fourth register table costs speed per CTA (measured −14 % at d = 7, 8) but may
+        // let one more CTA fit per SM (+62 % at d = 10, B = 3)
+        // (at 255 registers per thread the register file holds two 128-thread CTAs, whatever shared memory allows)
+        const auto ctas = [&](size_t bytes) { return std::min<size_t>(2, sm_smem / bytes); };
+        if (g && LL >= 4 && b <= limit && (a > limit || ctas(b) > ctas(a))) return 3;
+        if (a <= limit) return 2;
+    }
     return 0;
 }
 
@@ -194,7 +203,7 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
     const int d = plan.basis.d, LL = leaf_depth(plan), nup = d - LL;
     LeafParams q{};
     q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
-    q.theta_stride = theta_stride; q.out_stride = out_stride; q.small_cta = plan.leaf_cta == 2;
+    q.theta_stride = theta_stride; q.out_stride = out_stride; q.small_cta = plan.leaf_cta >= 2 ? plan.leaf_cta : 0;
     q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];

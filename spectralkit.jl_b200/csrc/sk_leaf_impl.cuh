@@ -290,22 +290,28 @@ struct LeafParams {
     const uint32_t *units;        // r | carry << 8
     const uint32_t *thmap;        // shared-memory slot of every coefficient (pair-aligned blocks, see leaf_end)
     int64_t n, K, n_units, Kslots;
-    int small_cta;                // use the 128-thread variant (chosen by the plan: shared-memory fit)
+    int small_cta;                // 0 full-size CTA; 2, 3: 128-thread variants (chosen by the plan: smolyak_leaf_cta)
     int64_t theta_stride, out_stride;   // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     int D, nup;
     sk_transform tr[SK_MAX_DIM];
 };
 
-enum { F_X0 = 0, F_X1, F_X2, F_X2D, F_T, F_TP, F_DT, F_DTP, F_ACC };   // upper-level fields, then ACC[0..D]
+enum { F_X0 = 0, F_X1, F_T, F_TP, F_DT, F_DTP, F_ACC };   // upper-level fields, then the level's accumulators
+// Upper level u (dimension LL+u+1) carries value + partials 1..LL+u+1 (gradient) or the value only: exactly that many
+// accumulators are kept (the state of all levels is what limits the CTAs per SM for high-dimensional bases).
+__host__ __device__ constexpr int up_ncomp(bool grad, int LL, int u) { return grad ? LL + u + 2 : 1; }
+__host__ __device__ constexpr int up_offset(bool grad, int LL, int u) {      // doubles of the levels below u
+    return grad ? u * (F_ACC + LL + 2) + u * (u - 1) / 2 : u * (F_ACC + 1);
+}
 
 // shared memory layout (bytes), shared by host and device
 struct LeafSmem {
     size_t stab, up, units, theta, total;
-    __host__ __device__ LeafSmem(int NT, int LL, int treg, int D, int nup, int64_t n_units, int64_t K) {
+    __host__ __device__ LeafSmem(int NT, int LL, int treg, int D, int nup, int64_t n_units, int64_t K, bool grad) {
         const int sdims = LL > treg ? LL - treg : 0;
         stab = 0;
         up = stab + (size_t)sdims * (kTab + 1) * NT * 16;
-        units = up + (size_t)nup * (F_ACC + D + 1) * NT * 8;
+        units = up + (size_t)up_offset(grad, LL, nup) * NT * 8;
         theta = units + (size_t)((n_units + 3) & ~(int64_t)3) * 4;
         total = theta + (size_t)K * 8;
     }
@@ -316,16 +322,15 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int D = q.D, NUP = q.nup;
-    const int NF = F_ACC + D + 1;
-    const LeafSmem lay(NT, LL, TREG, D, NUP, q.n_units, q.Kslots);
+    const LeafSmem lay(NT, LL, TREG, D, NUP, q.n_units, q.Kslots, GRAD);
     double2 *stab = reinterpret_cast<double2 *>(smem_raw + lay.stab) + tid;
-    double *up = reinterpret_cast<double *>(smem_raw + lay.up);           // [NUP][NF][threads]
+    double *up = reinterpret_cast<double *>(smem_raw + lay.up);           // [level: fields, accumulators][threads]
     uint32_t *s_units = reinterpret_cast<uint32_t *>(smem_raw + lay.units);
     double *s_theta = reinterpret_cast<double *>(smem_raw + lay.theta);
     for (int64_t i = tid; i < q.n_units; i += NT) s_units[i] = q.units[i];
     for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i * q.theta_stride];
     __syncthreads();
-#define UP(u, f) up[((size_t)(u) * NF + (f)) * NT + tid]
+#define UP(u, f) up[(size_t)(up_offset(GRAD, LL, (u)) + (f)) * NT + tid]
     constexpr int NCL = NC<GRAD, LL>::value;
     const int E = GRAD ? D + 1 : 1;
 
@@ -368,8 +373,8 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
         for (int u = 0; u < NUP; u++) {
             double xj[GRAD ? 2 : 1];
             skd::to_pm1_jet<GRAD ? 2 : 1>(q.tr[LL + u], __ldcs(xp + LL + u), xj);
-            UP(u, F_X0) = xj[0]; UP(u, F_X2) = 2.0 * xj[0];
-            if (GRAD) { UP(u, F_X1) = xj[GRAD ? 1 : 0]; UP(u, F_X2D) = 2.0 * xj[GRAD ? 1 : 0]; }
+            UP(u, F_X0) = xj[0];
+            if (GRAD) UP(u, F_X1) = xj[GRAD ? 1 : 0];
         }
         uint32_t first = 0xFFFFFFFFu;                       // bit u: upper level u sits at index 1
         const double *ub = s_theta;                         // aligned block of the current unit
@@ -419,11 +424,11 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
                             if (GRAD) { UP(u, F_DTP) = 0.0; UP(u, F_DT) = UP(u, F_X1); }
                             first &= ~(1u << u);
                         } else {
-                            const double X2 = UP(u, F_X2), Tc = UP(u, F_T), Tq = UP(u, F_TP);
+                            const double X2 = 2.0 * UP(u, F_X0), Tc = UP(u, F_T), Tq = UP(u, F_TP);
                             UP(u, F_T) = fma(X2, Tc, -Tq); UP(u, F_TP) = Tc;
                             if (GRAD) {
                                 const double dTc = UP(u, F_DT);
-                                UP(u, F_DT) = fma(X2, dTc, fma(UP(u, F_X2D), Tc, -UP(u, F_DTP)));
+                                UP(u, F_DT) = fma(X2, dTc, fma(2.0 * UP(u, F_X1), Tc, -UP(u, F_DTP)));
                                 UP(u, F_DTP) = dTc;
                             }
                         }
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
 template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
     auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT>;
-    const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.Kslots);
+    const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.Kslots, GRAD);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -480,7 +485,8 @@ constexpr int leaf_nt_c(int LL, bool grad) { return LL >= 5 ? (grad ? 384 : 512)
 // thread and level, which does not fit next to the tables of a 256..512-thread CTA.  128 threads have 255 registers
 // each, so one more dimension's table moves to registers.
 constexpr int kLeafSmallNT = 128;
-constexpr int leaf_treg_small_c(int LL, bool grad) { const int t = grad ? 3 : 4; return LL < t ? LL : t; }
+// register tables of the small CTAs: 3 (gradient) / 4 dimensions, or 4 for both when that lets one more CTA fit per SM
+constexpr int leaf_treg_small_c(int LL, bool grad, bool lean = false) { const int t = grad && !lean ? 3 : 4; return LL < t ? LL : t; }
 constexpr int leaf_sync_c(int) { return 0; }       // CTA re-convergence granularity (terms); measured: no gain
 constexpr int leaf_loopd_c(int LL, bool grad) { return grad && LL >= 5 ? LL : 99; }   // first dimension walked by per-block runtime loops
 
@@ -499,6 +505,15 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
         }
     }
 #endif
+    if (q.small_cta == 3) {      // gradient, four register tables: smaller shared-memory footprint, more CTAs per SM
+        if constexpr (GRAD) {
+            switch (LL) {
+            case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_small_c(4, GRAD, true), 1, 0, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
+            case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_small_c(6, GRAD, true), 1, 0, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
+            }
+        }
+        return cudaErrorInvalidValue;
+    }
     if (q.small_cta) {      // LL in {2, 4, 6} are the depths that occur together with upper dimensions (leaf_rmax_c)
         switch (LL) {
         case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_small_c(2, GRAD), 1, 0, leaf_loopd_c(2, GRAD), kLeafSmallNT>(q, stream);
