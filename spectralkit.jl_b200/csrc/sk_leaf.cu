@@ -107,8 +107,9 @@ int smolyak_leaf_cta(const sk_plan &plan) {
         // let one more CTA fit per SM (+62 % at d = 10, B = 3)
         // (at 255 registers per thread the register file holds two 128-thread CTAs, whatever shared memory allows)
         const auto ctas = [&](size_t bytes) { return std::min<size_t>(2, sm_smem / bytes); };
-        if (g && LL >= 4 && b <= limit && (a > limit || ctas(b) > ctas(a))) return 3;
-        if (a <= limit) return 2;
+        const size_t cap = 226 * 1024;      // a CTA may use up to 227 KB of dynamic shared memory
+        if (g && LL >= 4 && b <= cap && (a > cap || ctas(b) > ctas(a))) return 3;
+        if (a <= cap) return 2;
     }
     return 0;
 }
