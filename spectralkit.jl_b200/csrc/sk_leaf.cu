@@ -169,7 +169,7 @@ double smolyak_leaf_flops(const sk_plan &plan) {
         const int r = (int)(w & 0xFF), c = (int)(w >> 8);
         f += leaf_flops_rec(S, LL, r, g, memo);
         if (nup == 0) continue;
-        if (!first[0]) f += g ? 2.0 * (LL + 2) : 2.0;
+        if (!first[0]) f += g ? (r == 0 ? 4.0 : 2.0 * (LL + 2)) : 2.0;     // budget-0 leaf: value and the new partial only
         for (int u = 0; u < nup; u++) {
             if (u < c) {
                 if (u + 1 < nup && !first[(size_t)u + 1]) f += g ? 2.0 * (LL + u + 3) : 2.0;

@@ -397,6 +397,11 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
 #pragma unroll
                     for (int m = 0; m < NCL; m++) UP(0, F_ACC + m) = a[m];
                     if (GRAD) UP(0, F_ACC + LL + 1) = 0.0;
+                } else if (r == 0) {
+                    // no budget left for the leaf: it is the single coefficient a[0], all its partials are structurally
+                    // zero (three quarters of the units of a high-dimensional basis)
+                    UP(0, F_ACC) = fma(UP(0, F_T), a[0], UP(0, F_ACC));
+                    if (GRAD) UP(0, F_ACC + LL + 1) = fma(UP(0, F_DT), a[0], UP(0, F_ACC + LL + 1));
                 } else {
                     const double Tv = UP(0, F_T);
 #pragma unroll
