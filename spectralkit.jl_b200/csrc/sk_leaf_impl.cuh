@@ -506,6 +506,8 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
             switch (v) {      // NB: LOOPD must equal leaf_loopd_c (the host's coefficient map depends on it)
             case 1: return launch_leaf<GK, 6, 4, GRAD, 2, 1, 0, 6, 352>(q, stream);
             case 2: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 6, 256>(q, stream);
+            case 3: return launch_leaf<GK, 6, 4, GRAD, 3, 1, 0, 6, 384>(q, stream);
+            case 4: return launch_leaf<GK, 6, 4, GRAD, 4, 1, 0, 6, 256>(q, stream);
             }
         }
     }
