@@ -704,3 +704,15 @@ def test_full_size_headline_properties(orc):
     want = orc.smolyak_lincomb(2, d, B, B, th1, ys, trs=otr, spec=ospec)
     scale = orc.smolyak_lincomb(2, d, B, B, th1, ys, trs=otr, spec=ospec, absmode=True)
     assert within(o1[sel].cpu().numpy(), want, scale)
+
+
+def test_randomised_parity_sweep():
+    # profiles/fuzz_parity.py walks the whole dispatch table with random configurations (8 000 of them are logged in
+    # profiles/r1_fuzz_parity.jsonl); a short sweep runs with the suite
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ge.ROOT, "profiles", "fuzz_parity.py"), "200", "77"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    summary = json.loads(out.stdout.strip().splitlines()[-1])
+    assert summary["failures"] == 0 and summary["worst_fast_scaled_error"] <= TAU, out.stdout[-2000:]
