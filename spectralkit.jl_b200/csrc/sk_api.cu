@@ -359,6 +359,10 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         p->flops_direct = (double)p->K * (C * (d - 1) + 2 * C) + ftab;
         p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
         if (!p->fast_kernel && p->fast_mode < 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+        // gradients the leaf kernel cannot serve (block cap M < B, θ too large): the generic nested kernel keeps its state
+        // in registers, which spill beyond 8 dimensions (d = 10, B = 3: 3.6 vs 8.9 Mpoints/s); the general kernel keeps it
+        // in shared memory
+        if (p->fast_kernel == 1 && p->fast_mode == 1 && d >= 9 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
         {   // experiments: SK_FORCE_GENERAL=1 sends every ∂ request the general kernel can serve to it
             static const int force = [] { const char *e = getenv("SK_FORCE_GENERAL"); return e ? atoi(e) : 0; }();
             if (force && p->ncomp > 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
