@@ -642,6 +642,24 @@ def linear_combination(basis, theta, x=None, *, exact: bool = False, device: int
     return out[0] if single else out
 
 
+def stacked_linear_combination(basis, coefficients, x, **kw):
+    """Several functions over one basis from ONE stacked coefficient vector, the layout of the reference's
+    `Experimental.make_policy_functions` (src/experimental.jl:156-166: function p owns `coefficients[(p-1)·K+1 : p·K]`,
+    K = dimension(basis)).  Returns (n, P): column p is `linear_combination(basis, coefficients[p·K:(p+1)·K], x)`,
+    evaluated in one pass as a K×P coefficient block."""
+    K = dimension(basis)
+    th = coefficients
+    total = int(th.shape[0]) if hasattr(th, "shape") else len(th)
+    if total == 0 or total % K != 0:
+        raise ArgumentError("length(coefficients) must be a positive multiple of dimension(basis)")
+    P = total // K
+    if _is_torch(th):
+        block = th.reshape(P, K).t().contiguous()
+    else:
+        block = np.ascontiguousarray(np.asarray(th, dtype=np.float64).reshape(P, K).T)
+    return linear_combination(basis, block, x, **kw)
+
+
 def basis_at(basis, x, *, device: int = 0, allow_rational_d2: bool = False):
     """Basis functions at the points: array (n, K[, E]) — row i is `collect(basis_at(basis, x[i]))`.
 

@@ -706,6 +706,22 @@ def test_full_size_headline_properties(orc):
     assert within(o1[sel].cpu().numpy(), want, scale)
 
 
+def test_stacked_coefficients_like_make_policy_functions(orc):
+    # src/experimental.jl:156-166: one coefficient vector, a range of dimension(basis) entries per policy function
+    rng = np.random.default_rng(12)
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 4) @ sk.coordinate_transformations(
+        sk.BoundedLinear(0, 4), sk.BoundedLinear(-2, 2), sk.SemiInfRational(1, 2), sk.InfRational(0, 4))
+    K, P = sk.dimension(basis), 3
+    coef = rng.standard_normal(K * P)
+    y = sk.transform_from(basis, basis.transformation, rng.uniform(-0.9, 0.9, (200, 4)))
+    got = sk.stacked_linear_combination(basis, coef, y)
+    assert got.shape == (200, P)
+    for p in range(P):
+        assert same(got[:, p], sk.linear_combination(basis, coef[p * K:(p + 1) * K].copy(), y))
+    with pytest.raises(sk.ArgumentError):
+        sk.stacked_linear_combination(basis, coef[:-1], y)
+
+
 def test_randomised_parity_sweep():
     # profiles/fuzz_parity.py walks the whole dispatch table with random configurations (8 000 of them are logged in
     # profiles/r1_fuzz_parity.jsonl); a short sweep runs with the suite
