@@ -423,7 +423,6 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
             CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             std::vector<uint32_t> thmap;
             p->theta_slots = skk::smolyak_leaf_theta_map(*p, &thmap);
-            p->leaf_cta = skk::smolyak_leaf_cta(*p);
             if ((int64_t)thmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
             CK(cudaMalloc(&p->d_thmap, thmap.size() * sizeof(uint32_t)));
             CK(cudaMemcpy(p->d_thmap, thmap.data(), thmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -87,6 +87,7 @@ struct sk_plan {
     int64_t n_units = 0;
     uint32_t *d_thmap = nullptr; // [K] shared-memory slot of every coefficient (unrolled-leaf kernel)
     int64_t theta_slots = 0;
+    int leaf_LL = 0;             // dimensions covered by the unrolled leaf (sk_leaf.cu: smolyak_leaf_supported)
     int leaf_cta = 0;            // 1 full-size CTA, 2 the 128-thread variant (sk_leaf.cu: smolyak_leaf_cta)
     uint32_t *d_bprog = nullptr; // factor program of the coefficient-block kernel (sk_block.cu)
     int bprog_F = 0, bprog_HL = 0;

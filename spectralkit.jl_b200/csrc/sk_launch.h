@@ -27,7 +27,7 @@ cudaError_t smolyak_nested_lincomb(const sk_plan &plan, const double *theta, con
 double smolyak_nested_flops(const sk_plan &plan);
 
 // ---- Smolyak, nested evaluation with compile-time unrolled leaves (sk_leaf.cu): the headline kernel
-bool smolyak_leaf_supported(const sk_plan &plan);
+bool smolyak_leaf_supported(sk_plan &plan);      // also fixes plan.leaf_LL / plan.leaf_cta
 int smolyak_leaf_cta(const sk_plan &plan);
 void smolyak_leaf_units(const sk_plan &plan, std::vector<uint32_t> &units);
 int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);

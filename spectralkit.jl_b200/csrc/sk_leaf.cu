@@ -14,19 +14,9 @@ cudaError_t dispatch_leaf_g1g(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g2v(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g2g(int LL, const LeafParams &q, cudaStream_t stream);
 
-// number of unrolled leaf dimensions for a plan: the deepest built leaf that covers the budget B.
-// SK_LEAF_LL=n caps it (experiments).
-static int leaf_depth(const sk_plan &plan) {
-    static const int cap = [] {
-        const char *e = getenv("SK_LEAF_LL");
-        int x = e ? atoi(e) : kLeafMaxLL;
-        return x >= 1 && x <= kLeafMaxLL ? x : kLeafMaxLL;
-    }();
-    const int d = plan.basis.d, B = plan.basis.B;
-    for (int LL = std::min(d, cap); LL >= 1; LL--)
-        if (B <= leaf_rmax_c(plan.basis.grid_kind, LL)) return LL;
-    return 0;
-}
+// number of unrolled leaf dimensions of a plan: chosen once by smolyak_leaf_supported (the deepest built leaf that
+// covers the budget B and whose state fits in shared memory) and stored in the plan
+static int leaf_depth(const sk_plan &plan) { return plan.leaf_LL; }
 
 // shared-memory slot of every coefficient: mirrors leaf_end / LeafBlocks of sk_leaf_impl.cuh (pair-aligned blocks
 // wherever a runtime loop changes the base); returns the slot after the last coefficient of Leaf<T, R>
@@ -75,17 +65,31 @@ int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) 
 static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
                                             double *out, int64_t out_stride, cudaStream_t stream);
 
-bool smolyak_leaf_supported(const sk_plan &plan) {
+// Decides whether the unrolled-leaf kernel serves the plan and, if so, fixes its leaf depth (plan.leaf_LL) and CTA
+// shape (plan.leaf_cta).  SK_LEAF_LL=n caps the depth (experiments).
+bool smolyak_leaf_supported(sk_plan &plan) {
+    plan.leaf_LL = 0; plan.leaf_cta = 0;
     if (plan.basis.kind != SK_BASIS_SMOLYAK || plan.fast_mode < 0) return false;
     if (plan.basis.M != plan.basis.B) return false;            // block cap below the budget: generic kernel
-    const int LL = leaf_depth(plan);
-    if (LL < 1) return false;
-    const int d = plan.basis.d, nup = d - LL;
-    if (nup > 12) return false;
-    int64_t n_units = 1;
-    if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
-    if (n_units * 2 + plan.K > 64 * 1024) return false;        // cannot fit anyway (and keeps the map cheap)
-    return smolyak_leaf_cta(plan) != 0;
+    static const int cap = [] {
+        const char *e = getenv("SK_LEAF_LL");
+        int x = e ? atoi(e) : kLeafMaxLL;
+        return x >= 1 && x <= kLeafMaxLL ? x : kLeafMaxLL;
+    }();
+    const int d = plan.basis.d, B = plan.basis.B;
+    for (int LL = std::min(d, cap); LL >= 1; LL--) {
+        if (!leaf_built_c(LL) || B > leaf_rmax_c(plan.basis.grid_kind, LL)) continue;
+        const int nup = d - LL;
+        if (nup > 12) break;
+        int64_t n_units = 1;
+        if (nup > 0) n_units = skh::smolyak_count(plan.basis.grid_kind, nup, plan.basis.B, plan.basis.M);
+        if (n_units * 2 + plan.K > 64 * 1024) continue;        // cannot fit anyway (and keeps the map cheap)
+        plan.leaf_LL = LL;
+        plan.leaf_cta = smolyak_leaf_cta(plan);
+        if (plan.leaf_cta) return true;                          // deepest leaf whose state fits in shared memory
+    }
+    plan.leaf_LL = 0;
+    return false;
 }
 
 // which CTA shape serves the plan: 1 = the tuned full-size CTA, 2 = the 128-thread variant (bases with upper

@@ -475,17 +475,23 @@ cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
 }
 
 // leaf depth / budget combinations that are built (code size and compile time bound the budget)
-constexpr int kLeafMaxLL = 6;
+// Depths 8 and 10 exist for the small budgets of high-dimensional bases: there the unit interpreter, not the
+// arithmetic, is the cost (profiles/r1_leaf_variants.md), and a leaf over 8 or 10 dimensions with budget <= 3 or 2 is
+// a few hundred terms of straight-line code.
+constexpr int kLeafMaxLL = 10;
+__host__ __device__ constexpr bool leaf_built_c(int LL) { return (LL >= 1 && LL <= 6) || LL == 8 || LL == 10; }
 __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
+    if (LL >= 9) return 2;
+    if (LL >= 7) return gk == SK_GRID_INTERIOR ? 2 : 3;
     if (gk == SK_GRID_INTERIOR) return LL <= 2 ? 4 : LL <= 4 ? 3 : 2;
     return LL <= 4 ? 5 : 4;
 }
 // tuning measured on B200 for the d = 6, B = 4 gradient case (profiles/r1_leaf_variants.md): 12 warps/SM at
 // 168 registers with two register tables and only the top dimension looped is the best trade between
 // latency hiding, spills and instruction-cache reuse
-constexpr int leaf_treg_c(int LL, bool grad) { const int t = grad ? (LL >= 5 ? 2 : 3) : (LL >= 5 ? 3 : 4); return LL < t ? LL : t; }
+constexpr int leaf_treg_c(int LL, bool grad) { const int t = LL >= 7 ? (grad ? 3 : 4) : grad ? (LL >= 5 ? 2 : 3) : (LL >= 5 ? 3 : 4); return LL < t ? LL : t; }
 constexpr int leaf_minb_c(int LL, bool grad) { return (LL >= 5 || (grad && LL >= 3)) ? 1 : 2; }
-constexpr int leaf_nt_c(int LL, bool grad) { return LL >= 5 ? (grad ? 384 : 512) : 256; }   // threads per CTA
+constexpr int leaf_nt_c(int LL, bool grad) { return LL >= 7 ? 128 : LL >= 5 ? (grad ? 384 : 512) : 256; }   // threads per CTA (deep leaves: 255 registers each)
 // small-CTA variants for bases with dimensions above the leaf (d > LL): the upper-level state is (9 + d) doubles per
 // thread and level, which does not fit next to the tables of a 256..512-thread CTA.  128 threads have 255 registers
 // each, so one more dimension's table moves to registers.
@@ -536,6 +542,8 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4, GRAD), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD), leaf_nt_c(4, GRAD)>(q, stream);
     case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5, GRAD), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD), leaf_nt_c(5, GRAD)>(q, stream);
     case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
+    case 8: return launch_leaf<GK, 8, leaf_rmax_c(GK, 8), GRAD, leaf_treg_c(8, GRAD), leaf_minb_c(8, GRAD), leaf_sync_c(8), leaf_loopd_c(8, GRAD), leaf_nt_c(8, GRAD)>(q, stream);
+    case 10: return launch_leaf<GK, 10, leaf_rmax_c(GK, 10), GRAD, leaf_treg_c(10, GRAD), leaf_minb_c(10, GRAD), leaf_sync_c(10), leaf_loopd_c(10, GRAD), leaf_nt_c(10, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
 }
