@@ -483,7 +483,7 @@ __host__ __device__ constexpr bool leaf_built_c(int LL) { return (LL >= 1 && LL 
 __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
     if (LL >= 9) return 2;
     if (LL >= 7) return gk == SK_GRID_INTERIOR ? 2 : 3;
-    if (gk == SK_GRID_INTERIOR) return LL <= 2 ? 4 : LL <= 4 ? 3 : 2;
+    if (gk == SK_GRID_INTERIOR) return LL <= 4 ? 4 : 3;             // ℓ = 3^b: 1 473 terms at (LL, R) = (4, 4), 737 at (6, 3)
     return LL <= 4 ? 5 : 4;
 }
 // tuning measured on B200 for the d = 6, B = 4 gradient case (profiles/r1_leaf_variants.md): 12 warps/SM at
