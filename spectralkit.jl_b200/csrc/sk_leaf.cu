@@ -13,6 +13,13 @@ cudaError_t dispatch_leaf_g1v(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g1g(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g2v(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g2g(int LL, const LeafParams &q, cudaStream_t stream);
+// single-budget kernels (sk_leaf_s*.cu); cudaErrorNotSupported when (LL, R) is not built
+cudaError_t dispatch_leaf_s0v(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_s0g(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_s1v(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_s1g(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_s2v(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_s2g(int LL, int R, const LeafParams &q, cudaStream_t stream);
 
 // number of unrolled leaf dimensions of a plan: chosen once by smolyak_leaf_supported (the deepest built leaf that
 // covers the budget B and whose state fits in shared memory) and stored in the plan
@@ -215,6 +222,17 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
     }
     const bool g = plan.fast_mode == 1;
+    static const bool no_single = getenv("SK_LEAF_NO_SINGLE") != nullptr;
+    if (nup == 0 && plan.n_units == 1 && !no_single) {      // the basis is one leaf of budget B: single-budget kernel when built
+        const int R = plan.basis.B;
+        cudaError_t e = cudaErrorNotSupported;
+        switch (plan.basis.grid_kind) {
+        case SK_GRID_INTERIOR: e = g ? dispatch_leaf_s0g(LL, R, q, stream) : dispatch_leaf_s0v(LL, R, q, stream); break;
+        case SK_GRID_ENDPOINT: e = g ? dispatch_leaf_s1g(LL, R, q, stream) : dispatch_leaf_s1v(LL, R, q, stream); break;
+        case SK_GRID_INTERIOR2: e = g ? dispatch_leaf_s2g(LL, R, q, stream) : dispatch_leaf_s2v(LL, R, q, stream); break;
+        }
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (plan.basis.grid_kind) {
     case SK_GRID_INTERIOR: return g ? dispatch_leaf_g0g(LL, q, stream) : dispatch_leaf_g0v(LL, q, stream);
     case SK_GRID_ENDPOINT: return g ? dispatch_leaf_g1g(LL, q, stream) : dispatch_leaf_g1v(LL, q, stream);

@@ -317,7 +317,10 @@ struct LeafSmem {
     }
 };
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
+// RONLY >= 0: single-budget kernel for bases that are one leaf of budget RONLY (d == LL).  The multi-budget kernel
+// holds the code of every budget <= RMAX and is register-allocated for the largest: at (LL, R) = (3, 3) it ran with
+// 254 registers and 268 spill stores per point (profiles/r1_leaf_variants.md, "single-budget kernels").
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1>
 __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -381,7 +384,10 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
         double a[NCL];
         for (int64_t un = 0; un < q.n_units; un++) {
             const uint32_t w = s_units[un];
-            const int r = (int)(w & 0xFF), c = (int)(w >> 8);
+            const int r = RONLY >= 0 ? RONLY : (int)(w & 0xFF), c = (int)(w >> 8);
+            if constexpr (RONLY >= 0) {
+                ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RONLY >= 0 ? RONLY : 0, CX>::run(cx, th, 0, a));
+            } else
             switch (r) {
             case 0: { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, 0, CX>::run(cx, th, 0, a)); } break;
             case 1: if constexpr (RMAX >= 1) { ThRd th{ub, 0.0}; ub += even_up(Leaf<GK, LL, RMAX >= 1 ? 1 : 0, CX>::run(cx, th, 0, a)); } break;
@@ -455,9 +461,9 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
 #undef UP
 }
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
-    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT>;
+    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT, RONLY>;
     const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.Kslots, GRAD);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -546,6 +552,55 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     case 10: return launch_leaf<GK, 10, leaf_rmax_c(GK, 10), GRAD, leaf_treg_c(10, GRAD), leaf_minb_c(10, GRAD), leaf_sync_c(10), leaf_loopd_c(10, GRAD), leaf_nt_c(10, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+// single-budget kernels (RONLY) for bases that are exactly one leaf (d == LL, one unit of budget B).  Built where they
+// beat the multi-budget kernel of the same depth (profiles/r1_leaf_variants.md, "single-budget kernels"): every
+// budget >= 2 for LL <= 4; budgets below the top one for LL = 5, 6 (the multi-budget kernels of those depths are
+// tuned for their top budget), except the (6, 3) gradient where the 384-thread multi-budget kernel stays ahead.
+// cudaErrorNotSupported = not built, the caller falls back to dispatch_leaf.
+constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
+    if (LL < 1 || LL > 6 || R < 2 || R > leaf_rmax_c(gk, LL)) return false;
+    if (LL <= 4) return true;
+    if (R == leaf_rmax_c(gk, LL)) return false;
+    return !(grad && LL == 6 && R == 3);
+}
+// measured choice per budget (variants A..E of the log): small budgets fit two CTAs of 256 threads per SM (<= 128
+// registers); from budget 3 (gradients; 4 for values) two register tables instead of three or four leave the registers
+// to the accumulators of the unrolled recursion
+constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
+    const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
+    return LL < t ? LL : t;
+}
+constexpr int leaf_single_minb_c(int gk, int R) { return R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
+template <int GK, bool GRAD, int LL, int R>
+cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
+    if constexpr (leaf_single_built_c(GK, LL, R, GRAD))
+        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_loopd_c(LL, GRAD), 256, R>(q, stream);
+    else
+        return cudaErrorNotSupported;
+}
+template <int GK, bool GRAD, int LL>
+cudaError_t dispatch_leaf_single_r(int R, const LeafParams &q, cudaStream_t stream) {
+    switch (R) {
+    case 2: return launch_leaf_single<GK, GRAD, LL, 2>(q, stream);
+    case 3: return launch_leaf_single<GK, GRAD, LL, 3>(q, stream);
+    case 4: return launch_leaf_single<GK, GRAD, LL, 4>(q, stream);
+    case 5: return launch_leaf_single<GK, GRAD, LL, 5>(q, stream);
+    }
+    return cudaErrorNotSupported;
+}
+template <int GK, bool GRAD>
+cudaError_t dispatch_leaf_single(int LL, int R, const LeafParams &q, cudaStream_t stream) {
+    switch (LL) {
+    case 1: return dispatch_leaf_single_r<GK, GRAD, 1>(R, q, stream);
+    case 2: return dispatch_leaf_single_r<GK, GRAD, 2>(R, q, stream);
+    case 3: return dispatch_leaf_single_r<GK, GRAD, 3>(R, q, stream);
+    case 4: return dispatch_leaf_single_r<GK, GRAD, 4>(R, q, stream);
+    case 5: return dispatch_leaf_single_r<GK, GRAD, 5>(R, q, stream);
+    case 6: return dispatch_leaf_single_r<GK, GRAD, 6>(R, q, stream);
+    }
+    return cudaErrorNotSupported;
 }
 
 }  // namespace skk

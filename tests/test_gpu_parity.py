@@ -254,6 +254,29 @@ def test_smolyak_exact_bit_identical(orc, code, d, B, M):
                     orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec))
 
 
+@pytest.mark.parametrize("code", [0, 1, 2])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6])
+def test_smolyak_single_budget_leaf_kernels(orc, code, d):
+    # bases that are one leaf (d <= 6) run budget-specific kernels for B = 2..5 (sk_leaf_impl.cuh: leaf_single_built_c);
+    # every one of them, values and gradient, ragged n and n = 1
+    for B in (2, 3, 4, 5):
+        basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+        K = sk.dimension(basis)
+        if K > 3000:
+            continue
+        rng = np.random.default_rng(7000 + code * 100 + d * 10 + B)
+        theta = rng.standard_normal(K)
+        for n in (1, 777):
+            x = rand_pm1(rng, (n, d))
+            want = orc.smolyak_lincomb(code, d, B, B, theta, x)[:, 0]
+            scale = orc.smolyak_lincomb(code, d, B, B, theta, x, absmode=True)[:, 0]
+            assert within(sk.linear_combination(basis, theta, x), want, scale)
+            ospec = orc.gradient_spec(d)
+            want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
+            scale = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec, absmode=True)
+            assert within(sk.linear_combination(basis, theta, sk.gradient(d)(x)), want, scale)
+
+
 @pytest.mark.parametrize("code,d,B,M", SMOLYAK_CASES + [(2, 6, 4, 4), (1, 8, 3, 3), (0, 5, 3, 3), (2, 10, 3, 3), (2, 4, 5, 5)])
 def test_smolyak_fast_within_tolerance(orc, code, d, B, M):
     rng = np.random.default_rng(code * 100 + d * 10 + B + 1)
