@@ -562,6 +562,9 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
 constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
     if (LL < 1 || LL > 6 || R < 2 || R > leaf_rmax_c(gk, LL)) return false;
     if (LL <= 4) return true;
+#ifdef SK_SINGLE_HEADLINE
+    if (gk == SK_GRID_INTERIOR2 && LL == 6 && R == 4 && grad) return true;
+#endif
     if (R == leaf_rmax_c(gk, LL)) return false;
     return !(grad && LL == 6 && R == 3);
 }
@@ -572,11 +575,12 @@ constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
     const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
     return LL < t ? LL : t;
 }
+constexpr int leaf_single_nt_c(int LL, int R, bool grad) { return LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }
 constexpr int leaf_single_minb_c(int gk, int R) { return R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
 template <int GK, bool GRAD, int LL, int R>
 cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
     if constexpr (leaf_single_built_c(GK, LL, R, GRAD))
-        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_loopd_c(LL, GRAD), 256, R>(q, stream);
+        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_loopd_c(LL, GRAD), leaf_single_nt_c(LL, R, GRAD), R>(q, stream);
     else
         return cudaErrorNotSupported;
 }
