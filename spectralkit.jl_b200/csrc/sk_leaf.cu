@@ -54,11 +54,18 @@ static int leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of
     return off;
 }
 
+// the basis is one leaf of budget B and a kernel for that budget alone is built (sk_leaf_s*.cu)
+static bool leaf_single_kernel(const sk_plan &plan) {
+    const int LL = leaf_depth(plan);
+    return leaf_single_enabled() && plan.basis.d == LL && leaf_single_built_c(plan.basis.grid_kind, LL, plan.basis.B, plan.fast_mode == 1);
+}
+
 // θ scatter map of the whole plan (units in traversal order, each starting an aligned block); returns the slot count
 int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) {
     const skh::SmolyakSet &S = plan.set;
     const int LL = leaf_depth(plan);
-    const int LOOPD = leaf_loopd_c(LL, plan.fast_mode == 1);
+    const bool g = plan.fast_mode == 1;
+    const int LOOPD = leaf_single_kernel(plan) ? leaf_single_loopd_c(plan.basis.grid_kind, LL, plan.basis.B, g) : leaf_loopd_c(LL, g);
     std::vector<int> blk_of((size_t)S.H + 2, S.M);
     for (int b = S.M - 1; b >= 0; b--) for (int64_t i = 1; i <= S.ell[(size_t)b]; i++) blk_of[(size_t)i] = b;
     std::vector<uint32_t> units;
@@ -85,7 +92,8 @@ bool smolyak_leaf_supported(sk_plan &plan) {
     }();
     const int d = plan.basis.d, B = plan.basis.B;
     for (int LL = std::min(d, cap); LL >= 1; LL--) {
-        if (!leaf_built_c(LL) || B > leaf_rmax_c(plan.basis.grid_kind, LL)) continue;
+        const bool single = LL == d && leaf_single_enabled() && leaf_single_built_c(plan.basis.grid_kind, LL, B, plan.fast_mode == 1);
+        if (!leaf_built_c(LL) || (B > leaf_rmax_c(plan.basis.grid_kind, LL) && !single)) continue;
         const int nup = d - LL;
         if (nup > 12) break;
         int64_t n_units = 1;
@@ -109,6 +117,10 @@ int smolyak_leaf_cta(const sk_plan &plan) {
     const bool g = plan.fast_mode == 1;
     const int64_t slots = smolyak_leaf_theta_map(plan, nullptr);
     const size_t limit = 200 * 1024;
+    if (leaf_single_kernel(plan)) {
+        const int gk = plan.basis.grid_kind, R = plan.basis.B;
+        return LeafSmem(leaf_single_nt_c(LL, R, g), LL, leaf_single_treg_c(gk, LL, R, g), d, 0, 1, slots, g).total <= limit ? 1 : 0;
+    }
     if (LeafSmem(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, slots, g).total <= limit) return 1;
     if (nup > 0 && (LL == 2 || LL == 4 || LL == 6)) {
         const size_t sm_smem = 227 * 1024;
@@ -222,8 +234,7 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
     }
     const bool g = plan.fast_mode == 1;
-    static const bool no_single = getenv("SK_LEAF_NO_SINGLE") != nullptr;
-    if (nup == 0 && plan.n_units == 1 && !no_single) {      // the basis is one leaf of budget B: single-budget kernel when built
+    if (leaf_single_kernel(plan)) {      // the basis is one leaf of budget B: single-budget kernel when built
         const int R = plan.basis.B;
         cudaError_t e = cudaErrorNotSupported;
         switch (plan.basis.grid_kind) {

@@ -559,8 +559,10 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
 // budget >= 2 for LL <= 4; budgets below the top one for LL = 5, 6 (the multi-budget kernels of those depths are
 // tuned for their top budget), except the (6, 3) gradient where the 384-thread multi-budget kernel stays ahead.
 // cudaErrorNotSupported = not built, the caller falls back to dispatch_leaf.
+inline bool leaf_single_enabled() { static const bool on = getenv("SK_LEAF_NO_SINGLE") == nullptr; return on; }
 constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
-    if (LL < 1 || LL > 6 || R < 2 || R > leaf_rmax_c(gk, LL)) return false;
+    if (LL < 1 || LL > 6 || R < 2 || R > (LL <= 4 ? 5 : leaf_rmax_c(gk, LL))) return false;
+    if (gk == SK_GRID_INTERIOR && R > 4) return false;      // ℓ(5) = 243 indices: beyond the front end's template recursion depth
     if (LL <= 4) return true;
 #ifdef SK_SINGLE_HEADLINE
     if (gk == SK_GRID_INTERIOR2 && LL == 6 && R == 4 && grad) return true;
@@ -571,16 +573,31 @@ constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
 // measured choice per budget (variants A..E of the log): small budgets fit two CTAs of 256 threads per SM (<= 128
 // registers); from budget 3 (gradients; 4 for values) two register tables instead of three or four leave the registers
 // to the accumulators of the unrolled recursion
+// Two-dimensional leaves with long index ranges (ℓ(R) > 27: InteriorGrid2 budget 5, InteriorGrid budget 4) walk
+// dimension 2 with one runtime loop per block (LeafBlocks) instead of unrolling it index by index: +47..85 %.  For
+// three and four dimensions, and for EndpointGrid, the unrolled code stays ahead (r1_leaf_variants.md).
+#ifndef SK_SL_TREG
+#define SK_SL_TREG 1
+#endif
+constexpr int leaf_ell_c(int gk, int b) {
+    return gk == SK_GRID_ENDPOINT ? ellc<SK_GRID_ENDPOINT>(b) : gk == SK_GRID_INTERIOR ? ellc<SK_GRID_INTERIOR>(b) : ellc<SK_GRID_INTERIOR2>(b);
+}
+constexpr bool leaf_single_looped_c(int gk, int LL, int R) { return LL == 2 && gk != SK_GRID_ENDPOINT && leaf_ell_c(gk, R) > 27; }
 constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
+    if (leaf_single_looped_c(gk, LL, R)) return LL - 1 < SK_SL_TREG ? LL - 1 : SK_SL_TREG;
     const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
     return LL < t ? LL : t;
+}
+// first looped dimension; the host's coefficient layout (smolyak_leaf_theta_map) follows it
+constexpr int leaf_single_loopd_c(int gk, int LL, int R, bool grad) {
+    return leaf_single_looped_c(gk, LL, R) ? leaf_single_treg_c(gk, LL, R, grad) + 1 : leaf_loopd_c(LL, grad);
 }
 constexpr int leaf_single_nt_c(int LL, int R, bool grad) { return LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }
 constexpr int leaf_single_minb_c(int gk, int R) { return R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
 template <int GK, bool GRAD, int LL, int R>
 cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
     if constexpr (leaf_single_built_c(GK, LL, R, GRAD))
-        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_loopd_c(LL, GRAD), leaf_single_nt_c(LL, R, GRAD), R>(q, stream);
+        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_single_loopd_c(GK, LL, R, GRAD), leaf_single_nt_c(LL, R, GRAD), R>(q, stream);
     else
         return cudaErrorNotSupported;
 }
