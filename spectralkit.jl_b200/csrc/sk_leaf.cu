@@ -119,7 +119,7 @@ int smolyak_leaf_cta(const sk_plan &plan) {
     const size_t limit = 200 * 1024;
     if (leaf_single_kernel(plan)) {
         const int gk = plan.basis.grid_kind, R = plan.basis.B;
-        return LeafSmem(leaf_single_nt_c(LL, R, g), LL, leaf_single_treg_c(gk, LL, R, g), d, 0, 1, slots, g).total <= limit ? 1 : 0;
+        return LeafSmem(leaf_single_nt_c(gk, LL, R, g), LL, leaf_single_treg_c(gk, LL, R, g), d, 0, 1, slots, g).total <= limit ? 1 : 0;
     }
     if (LeafSmem(leaf_nt_c(LL, g), LL, leaf_treg_c(LL, g), d, nup, n_units, slots, g).total <= limit) return 1;
     if (nup > 0 && (LL == 2 || LL == 4 || LL == 6)) {

@@ -561,6 +561,10 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
 // cudaErrorNotSupported = not built, the caller falls back to dispatch_leaf.
 inline bool leaf_single_enabled() { static const bool on = getenv("SK_LEAF_NO_SINGLE") == nullptr; return on; }
 constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
+    // InteriorGrid (ℓ = 3^b) budget 4 at five and six dimensions (2 641 / 4 361 terms) exists only here: inside a
+    // multi-budget kernel it slowed every smaller budget (register allocation for the largest)
+    if (gk == SK_GRID_INTERIOR && (LL == 5 || LL == 6) && R == 4) return true;
+    if (gk != SK_GRID_INTERIOR && (LL == 5 || LL == 6) && R == 5) return true;      // 2 203..10 625 terms
     if (LL < 1 || LL > 6 || R < 2 || R > (LL <= 4 ? 5 : leaf_rmax_c(gk, LL))) return false;
     if (gk == SK_GRID_INTERIOR && R > 4) return false;      // ℓ(5) = 243 indices: beyond the front end's template recursion depth
     if (LL <= 4) return true;
@@ -585,6 +589,7 @@ constexpr int leaf_ell_c(int gk, int b) {
 constexpr bool leaf_single_looped_c(int gk, int LL, int R) { return LL == 2 && gk != SK_GRID_ENDPOINT && leaf_ell_c(gk, R) > 27; }
 constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
     if (leaf_single_looped_c(gk, LL, R)) return LL - 1 < SK_SL_TREG ? LL - 1 : SK_SL_TREG;
+    if (gk == SK_GRID_INTERIOR2 && LL == 6 && R == 5) return 3;      // θ (85 KB) + three shared-memory tables fit, four do not
     const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
     return LL < t ? LL : t;
 }
@@ -592,12 +597,16 @@ constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
 constexpr int leaf_single_loopd_c(int gk, int LL, int R, bool grad) {
     return leaf_single_looped_c(gk, LL, R) ? leaf_single_treg_c(gk, LL, R, grad) + 1 : leaf_loopd_c(LL, grad);
 }
-constexpr int leaf_single_nt_c(int LL, int R, bool grad) { return LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }
+#ifdef SK_SINGLE_HEADLINE
+constexpr int leaf_single_nt_c(int gk, int LL, int R, bool grad) { return gk == SK_GRID_INTERIOR2 && LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }
+#else
+constexpr int leaf_single_nt_c(int, int, int, bool) { return 256; }
+#endif
 constexpr int leaf_single_minb_c(int gk, int R) { return R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
 template <int GK, bool GRAD, int LL, int R>
 cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
     if constexpr (leaf_single_built_c(GK, LL, R, GRAD))
-        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_single_loopd_c(GK, LL, R, GRAD), leaf_single_nt_c(LL, R, GRAD), R>(q, stream);
+        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_single_loopd_c(GK, LL, R, GRAD), leaf_single_nt_c(GK, LL, R, GRAD), R>(q, stream);
     else
         return cudaErrorNotSupported;
 }
