@@ -228,7 +228,7 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
     LeafParams q{};
     q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
     q.theta_stride = theta_stride; q.out_stride = out_stride; q.small_cta = plan.leaf_cta >= 2 ? plan.leaf_cta : 0;
-    q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup;
+    q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup; q.budget = plan.basis.B;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }

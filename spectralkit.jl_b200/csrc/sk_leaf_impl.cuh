@@ -293,6 +293,7 @@ struct LeafParams {
     int small_cta;                // 0 full-size CTA; 2, 3: 128-thread variants (chosen by the plan: smolyak_leaf_cta)
     int64_t theta_stride, out_stride;   // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     int D, nup;
+    int budget;                   // B of the plan: no unit has a larger r
     sk_transform tr[SK_MAX_DIM];
 };
 
@@ -507,6 +508,16 @@ constexpr int leaf_treg_small_c(int LL, bool grad, bool lean = false) { const in
 constexpr int leaf_sync_c(int) { return 0; }       // CTA re-convergence granularity (terms); measured: no gain
 constexpr int leaf_loopd_c(int LL, bool grad) { return grad && LL >= 5 ? LL : 99; }   // first dimension walked by per-block runtime loops
 
+// Bases with dimensions above the leaf: the kernel holds the leaf code of every budget <= RMAX and is register-allocated
+// for the largest, so plans with budget 2 or 3 get instantiations that stop there (same reason as RONLY above).
+template <int GK, int LL, bool GRAD, int TREG, int MINB, int LOOPD, int NT>
+cudaError_t launch_leaf_budget(const LeafParams &q, cudaStream_t stream) {
+    constexpr int RM = leaf_rmax_c(GK, LL);
+    if constexpr (RM > 2) if (q.budget <= 2) return launch_leaf<GK, LL, 2, GRAD, TREG, MINB, 0, LOOPD, NT>(q, stream);
+    if constexpr (RM > 3) if (q.budget <= 3) return launch_leaf<GK, LL, 3, GRAD, TREG, MINB, 0, LOOPD, NT>(q, stream);
+    return launch_leaf<GK, LL, RM, GRAD, TREG, MINB, 0, LOOPD, NT>(q, stream);
+}
+
 // one dispatcher per (family, GRAD), each in its own translation unit (sk_leaf_g*.cu)
 template <int GK, bool GRAD>
 cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
@@ -527,17 +538,17 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     if (q.small_cta == 3) {      // gradient, four register tables: smaller shared-memory footprint, more CTAs per SM
         if constexpr (GRAD) {
             switch (LL) {
-            case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_small_c(4, GRAD, true), 1, 0, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
-            case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_small_c(6, GRAD, true), 1, 0, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
+            case 4: return launch_leaf_budget<GK, 4, GRAD, leaf_treg_small_c(4, GRAD, true), 1, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
+            case 6: return launch_leaf_budget<GK, 6, GRAD, leaf_treg_small_c(6, GRAD, true), 1, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
             }
         }
         return cudaErrorInvalidValue;
     }
     if (q.small_cta) {      // LL in {2, 4, 6} are the depths that occur together with upper dimensions (leaf_rmax_c)
         switch (LL) {
-        case 2: return launch_leaf<GK, 2, leaf_rmax_c(GK, 2), GRAD, leaf_treg_small_c(2, GRAD), 1, 0, leaf_loopd_c(2, GRAD), kLeafSmallNT>(q, stream);
-        case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_small_c(4, GRAD), 1, 0, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
-        case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_small_c(6, GRAD), 1, 0, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
+        case 2: return launch_leaf_budget<GK, 2, GRAD, leaf_treg_small_c(2, GRAD), 1, leaf_loopd_c(2, GRAD), kLeafSmallNT>(q, stream);
+        case 4: return launch_leaf_budget<GK, 4, GRAD, leaf_treg_small_c(4, GRAD), 1, leaf_loopd_c(4, GRAD), kLeafSmallNT>(q, stream);
+        case 6: return launch_leaf_budget<GK, 6, GRAD, leaf_treg_small_c(6, GRAD), 1, leaf_loopd_c(6, GRAD), kLeafSmallNT>(q, stream);
         }
         return cudaErrorInvalidValue;
     }
@@ -548,7 +559,7 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4, GRAD), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD), leaf_nt_c(4, GRAD)>(q, stream);
     case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5, GRAD), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD), leaf_nt_c(5, GRAD)>(q, stream);
     case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
-    case 8: return launch_leaf<GK, 8, leaf_rmax_c(GK, 8), GRAD, leaf_treg_c(8, GRAD), leaf_minb_c(8, GRAD), leaf_sync_c(8), leaf_loopd_c(8, GRAD), leaf_nt_c(8, GRAD)>(q, stream);
+    case 8: return launch_leaf_budget<GK, 8, GRAD, leaf_treg_c(8, GRAD), leaf_minb_c(8, GRAD), leaf_loopd_c(8, GRAD), leaf_nt_c(8, GRAD)>(q, stream);
     case 10: return launch_leaf<GK, 10, leaf_rmax_c(GK, 10), GRAD, leaf_treg_c(10, GRAD), leaf_minb_c(10, GRAD), leaf_sync_c(10), leaf_loopd_c(10, GRAD), leaf_nt_c(10, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
