@@ -139,6 +139,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner / debug lines stay off stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
