@@ -576,7 +576,7 @@ constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
     // multi-budget kernel it slowed every smaller budget (register allocation for the largest)
     if (gk == SK_GRID_INTERIOR && (LL == 5 || LL == 6) && R == 4) return true;
     if (gk != SK_GRID_INTERIOR && (LL == 5 || LL == 6) && R == 5) return true;      // 2 203..10 625 terms
-    if (LL < 1 || LL > 6 || R < 2 || R > (LL <= 4 ? 5 : leaf_rmax_c(gk, LL))) return false;
+    if (LL < 1 || LL > 6 || R < 1 || R > (LL <= 4 ? 5 : leaf_rmax_c(gk, LL))) return false;
     if (gk == SK_GRID_INTERIOR && R > 4) return false;      // ℓ(5) = 243 indices: beyond the front end's template recursion depth
     if (LL <= 4) return true;
 #ifdef SK_SINGLE_HEADLINE
@@ -624,6 +624,7 @@ cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
 template <int GK, bool GRAD, int LL>
 cudaError_t dispatch_leaf_single_r(int R, const LeafParams &q, cudaStream_t stream) {
     switch (R) {
+    case 1: return launch_leaf_single<GK, GRAD, LL, 1>(q, stream);
     case 2: return launch_leaf_single<GK, GRAD, LL, 2>(q, stream);
     case 3: return launch_leaf_single<GK, GRAD, LL, 3>(q, stream);
     case 4: return launch_leaf_single<GK, GRAD, LL, 4>(q, stream);

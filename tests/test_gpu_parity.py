@@ -257,9 +257,9 @@ def test_smolyak_exact_bit_identical(orc, code, d, B, M):
 @pytest.mark.parametrize("code", [0, 1, 2])
 @pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6])
 def test_smolyak_single_budget_leaf_kernels(orc, code, d):
-    # bases that are one leaf (d <= 6) run budget-specific kernels for B = 2..5 (sk_leaf_impl.cuh: leaf_single_built_c);
+    # bases that are one leaf (d <= 6) run budget-specific kernels for B = 1..5 (sk_leaf_impl.cuh: leaf_single_built_c);
     # every one of them, values and gradient, ragged n and n = 1
-    for B in (2, 3, 4, 5):
+    for B in (1, 2, 3, 4, 5):
         basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
         K = sk.dimension(basis)
         if K > 12000:
