@@ -482,11 +482,13 @@ cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
 }
 
 // leaf depth / budget combinations that are built (code size and compile time bound the budget)
+// Depths 12, 14 and 16 (budget <= 2, a few hundred terms) do the same for d = 11..16: d = 16, B = 2 went from 64 to
+// 2 300 Mpoints/s (value + gradient) once no dimension was left to the interpreter.
 // Depths 8 and 10 exist for the small budgets of high-dimensional bases: there the unit interpreter, not the
 // arithmetic, is the cost (profiles/r1_leaf_variants.md), and a leaf over 8 or 10 dimensions with budget <= 3 or 2 is
 // a few hundred terms of straight-line code.
-constexpr int kLeafMaxLL = 10;
-__host__ __device__ constexpr bool leaf_built_c(int LL) { return (LL >= 1 && LL <= 6) || LL == 8 || LL == 10; }
+constexpr int kLeafMaxLL = 16;
+__host__ __device__ constexpr bool leaf_built_c(int LL) { return (LL >= 1 && LL <= 6) || LL == 8 || LL == 10 || LL == 12 || LL == 14 || LL == 16; }
 __host__ __device__ constexpr int leaf_rmax_c(int gk, int LL) {
     if (LL >= 9) return 2;
     if (LL >= 7) return gk == SK_GRID_INTERIOR ? 2 : 3;
@@ -561,6 +563,9 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
     case 8: return launch_leaf_budget<GK, 8, GRAD, leaf_treg_c(8, GRAD), leaf_minb_c(8, GRAD), leaf_loopd_c(8, GRAD), leaf_nt_c(8, GRAD)>(q, stream);
     case 10: return launch_leaf<GK, 10, leaf_rmax_c(GK, 10), GRAD, leaf_treg_c(10, GRAD), leaf_minb_c(10, GRAD), leaf_sync_c(10), leaf_loopd_c(10, GRAD), leaf_nt_c(10, GRAD)>(q, stream);
+    case 12: return launch_leaf<GK, 12, leaf_rmax_c(GK, 12), GRAD, leaf_treg_c(12, GRAD), leaf_minb_c(12, GRAD), leaf_sync_c(12), leaf_loopd_c(12, GRAD), leaf_nt_c(12, GRAD)>(q, stream);
+    case 14: return launch_leaf<GK, 14, leaf_rmax_c(GK, 14), GRAD, leaf_treg_c(14, GRAD), leaf_minb_c(14, GRAD), leaf_sync_c(14), leaf_loopd_c(14, GRAD), leaf_nt_c(14, GRAD)>(q, stream);
+    case 16: return launch_leaf<GK, 16, leaf_rmax_c(GK, 16), GRAD, leaf_treg_c(16, GRAD), leaf_minb_c(16, GRAD), leaf_sync_c(16), leaf_loopd_c(16, GRAD), leaf_nt_c(16, GRAD)>(q, stream);
     }
     return cudaErrorInvalidValue;
 }
