@@ -8,7 +8,7 @@ import __graft_entry__ as ge
 sk = ge.load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 21
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for d, B in ((6, 4), (7, 2), (7, 3), (7, 4), (8, 2), (8, 3), (8, 4), (9, 2), (9, 3), (10, 3), (10, 2), (11, 2), (12, 2), (12, 3), (13, 2), (14, 2), (15, 2), (16, 2), (5, 5)):
+for d, B in ((6, 4), (7, 2), (7, 3), (7, 4), (8, 2), (8, 3), (8, 4), (9, 2), (9, 3), (10, 3), (10, 2), (11, 2), (11, 3), (12, 2), (12, 3), (13, 2), (14, 2), (15, 2), (16, 2), (5, 5)):
     basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
     K = sk.dimension(basis)
     th = torch.as_tensor(np.random.default_rng(1).standard_normal(K)).cuda()

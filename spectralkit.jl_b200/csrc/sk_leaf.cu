@@ -20,6 +20,11 @@ cudaError_t dispatch_leaf_s1v(int LL, int R, const LeafParams &q, cudaStream_t s
 cudaError_t dispatch_leaf_s1g(int LL, int R, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_s2v(int LL, int R, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_s2g(int LL, int R, const LeafParams &q, cudaStream_t stream);
+// deep single-budget kernels (sk_leaf_t*.cu)
+cudaError_t dispatch_leaf_t1v(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_t1g(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_t2v(int LL, int R, const LeafParams &q, cudaStream_t stream);
+cudaError_t dispatch_leaf_t2g(int LL, int R, const LeafParams &q, cudaStream_t stream);
 
 // number of unrolled leaf dimensions of a plan: chosen once by smolyak_leaf_supported (the deepest built leaf that
 // covers the budget B and whose state fits in shared memory) and stored in the plan
@@ -93,7 +98,7 @@ bool smolyak_leaf_supported(sk_plan &plan) {
     const int d = plan.basis.d, B = plan.basis.B;
     for (int LL = std::min(d, cap); LL >= 1; LL--) {
         const bool single = LL == d && leaf_single_enabled() && leaf_single_built_c(plan.basis.grid_kind, LL, B, plan.fast_mode == 1);
-        if (!leaf_built_c(LL) || (B > leaf_rmax_c(plan.basis.grid_kind, LL) && !single)) continue;
+        if (!single && (!leaf_built_c(LL) || B > leaf_rmax_c(plan.basis.grid_kind, LL))) continue;
         const int nup = d - LL;
         if (nup > 12) break;
         int64_t n_units = 1;
@@ -237,6 +242,12 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
     if (leaf_single_kernel(plan)) {      // the basis is one leaf of budget B: single-budget kernel when built
         const int R = plan.basis.B;
         cudaError_t e = cudaErrorNotSupported;
+        if (LL > 6) {
+            switch (plan.basis.grid_kind) {
+            case SK_GRID_ENDPOINT: e = g ? dispatch_leaf_t1g(LL, R, q, stream) : dispatch_leaf_t1v(LL, R, q, stream); break;
+            case SK_GRID_INTERIOR2: e = g ? dispatch_leaf_t2g(LL, R, q, stream) : dispatch_leaf_t2v(LL, R, q, stream); break;
+            }
+        } else
         switch (plan.basis.grid_kind) {
         case SK_GRID_INTERIOR: e = g ? dispatch_leaf_s0g(LL, R, q, stream) : dispatch_leaf_s0v(LL, R, q, stream); break;
         case SK_GRID_ENDPOINT: e = g ? dispatch_leaf_s1g(LL, R, q, stream) : dispatch_leaf_s1v(LL, R, q, stream); break;

@@ -576,7 +576,15 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
 // tuned for their top budget), except the (6, 3) gradient where the 384-thread multi-budget kernel stays ahead.
 // cudaErrorNotSupported = not built, the caller falls back to dispatch_leaf.
 inline bool leaf_single_enabled() { static const bool on = getenv("SK_LEAF_NO_SINGLE") == nullptr; return on; }
+// deep single leaves (EndpointGrid, InteriorGrid2; instantiated in sk_leaf_t*.cu): budget 3 at d = 7..12 except d = 8,
+// which the depth-8 multi-budget kernel is tuned for (d = 10, B = 3, ten state variables at level 3, is the classic
+// Smolyak setting), and budget 4 at d = 7, 8
+constexpr bool leaf_single_deep_c(int gk, int LL, int R) {
+    if (gk == SK_GRID_INTERIOR) return false;
+    return (R == 3 && LL >= 7 && LL <= 12 && LL != 8) || (R == 4 && (LL == 7 || LL == 8));
+}
 constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
+    if (leaf_single_deep_c(gk, LL, R)) return true;
     // InteriorGrid (ℓ = 3^b) budget 4 at five and six dimensions (2 641 / 4 361 terms) exists only here: inside a
     // multi-budget kernel it slowed every smaller budget (register allocation for the largest)
     if (gk == SK_GRID_INTERIOR && (LL == 5 || LL == 6) && R == 4) return true;
@@ -604,6 +612,7 @@ constexpr int leaf_ell_c(int gk, int b) {
 }
 constexpr bool leaf_single_looped_c(int gk, int LL, int R) { return LL == 2 && gk != SK_GRID_ENDPOINT && leaf_ell_c(gk, R) > 27; }
 constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
+    if (LL > 6) return leaf_treg_c(LL, grad);
     if (leaf_single_looped_c(gk, LL, R)) return LL - 1 < SK_SL_TREG ? LL - 1 : SK_SL_TREG;
     if (gk == SK_GRID_INTERIOR2 && LL == 6 && R == 5) return 3;      // θ (85 KB) + three shared-memory tables fit, four do not
     const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
@@ -616,13 +625,13 @@ constexpr int leaf_single_loopd_c(int gk, int LL, int R, bool grad) {
 #ifdef SK_SINGLE_HEADLINE
 constexpr int leaf_single_nt_c(int gk, int LL, int R, bool grad) { return gk == SK_GRID_INTERIOR2 && LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }
 #else
-constexpr int leaf_single_nt_c(int, int, int, bool) { return 256; }
+constexpr int leaf_single_nt_c(int, int LL, int, bool grad) { return LL > 6 ? leaf_nt_c(LL, grad) : 256; }
 #endif
-constexpr int leaf_single_minb_c(int gk, int R) { return R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
+constexpr int leaf_single_minb_c(int gk, int R, int LL = 1) { return LL > 6 ? 1 : R <= 3 || (R == 4 && gk == SK_GRID_ENDPOINT) ? 2 : 1; }
 template <int GK, bool GRAD, int LL, int R>
 cudaError_t launch_leaf_single(const LeafParams &q, cudaStream_t stream) {
     if constexpr (leaf_single_built_c(GK, LL, R, GRAD))
-        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R), 0, leaf_single_loopd_c(GK, LL, R, GRAD), leaf_single_nt_c(GK, LL, R, GRAD), R>(q, stream);
+        return launch_leaf<GK, LL, R, GRAD, leaf_single_treg_c(GK, LL, R, GRAD), leaf_single_minb_c(GK, R, LL), 0, leaf_single_loopd_c(GK, LL, R, GRAD), leaf_single_nt_c(GK, LL, R, GRAD), R>(q, stream);
     else
         return cudaErrorNotSupported;
 }
@@ -634,6 +643,21 @@ cudaError_t dispatch_leaf_single_r(int R, const LeafParams &q, cudaStream_t stre
     case 3: return launch_leaf_single<GK, GRAD, LL, 3>(q, stream);
     case 4: return launch_leaf_single<GK, GRAD, LL, 4>(q, stream);
     case 5: return launch_leaf_single<GK, GRAD, LL, 5>(q, stream);
+    }
+    return cudaErrorNotSupported;
+}
+template <int GK, bool GRAD>
+cudaError_t dispatch_leaf_single_deep(int LL, int R, const LeafParams &q, cudaStream_t stream) {
+    if (R == 3) switch (LL) {
+    case 7: return launch_leaf_single<GK, GRAD, 7, 3>(q, stream);
+    case 9: return launch_leaf_single<GK, GRAD, 9, 3>(q, stream);
+    case 10: return launch_leaf_single<GK, GRAD, 10, 3>(q, stream);
+    case 11: return launch_leaf_single<GK, GRAD, 11, 3>(q, stream);
+    case 12: return launch_leaf_single<GK, GRAD, 12, 3>(q, stream);
+    }
+    if (R == 4) switch (LL) {
+    case 7: return launch_leaf_single<GK, GRAD, 7, 4>(q, stream);
+    case 8: return launch_leaf_single<GK, GRAD, 8, 4>(q, stream);
     }
     return cudaErrorNotSupported;
 }

@@ -278,7 +278,8 @@ def test_smolyak_single_budget_leaf_kernels(orc, code, d):
 
 
 @pytest.mark.parametrize("code,d,B,M", SMOLYAK_CASES + [(2, 6, 4, 4), (1, 8, 3, 3), (0, 5, 3, 3), (2, 10, 3, 3), (2, 4, 5, 5),
-                                                       (2, 12, 2, 2), (0, 13, 2, 2), (1, 16, 2, 2), (2, 16, 2, 2), (2, 11, 2, 2), (2, 14, 2, 2), (1, 15, 2, 2)])
+                                                       (2, 12, 2, 2), (0, 13, 2, 2), (1, 16, 2, 2), (2, 16, 2, 2), (2, 11, 2, 2), (2, 14, 2, 2), (1, 15, 2, 2),
+                                                       (2, 7, 3, 3), (1, 9, 3, 3), (1, 10, 3, 3), (2, 11, 3, 3), (2, 12, 3, 3), (1, 12, 3, 3), (2, 7, 4, 4), (1, 8, 4, 4), (2, 8, 4, 4)])
 def test_smolyak_fast_within_tolerance(orc, code, d, B, M):
     rng = np.random.default_rng(code * 100 + d * 10 + B + 1)
     basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B, M), d)
