@@ -20,8 +20,8 @@ bad, worst, paths = 0, 0.0, {}
 t0 = time.time()
 for it in range(N):
     code = int(rng.integers(0, 3))
-    d = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]))
-    Bmax = {0: 3, 1: 4, 2: 4}[code] if d <= 6 else (2 if d >= 9 else 3)
+    d = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16]))
+    Bmax = {0: 4, 1: 5, 2: 5}[code] if d <= 6 else (4 if d <= 8 else 3 if d <= 12 else 2)      # K <= 6000 filters below
     B = int(rng.integers(0, Bmax + 1))
     M = B if rng.random() < 0.8 else int(rng.integers(0, B + 1))
     if orc.smolyak_length(code, d, B, M) > 6000:
@@ -70,7 +70,11 @@ for it in range(N):
     scale = orc.smolyak_lincomb(code, d, B, M, theta, y, trs=trs_or, spec=ospec, absmode=True)
     fp = int(sk.get_plan(basis, 0, spec).info.fast_path)
     paths[(kind, fp)] = paths.get((kind, fp), 0) + 1
-    ex = np.asarray(sk.linear_combination(basis, theta, pts, exact=True)).reshape(want.shape)
+    try:
+        ex = np.asarray(sk.linear_combination(basis, theta, pts, exact=True)).reshape(want.shape)
+    except sk.UnsupportedError:      # tables of the bit-identical direct kernel exceed shared memory (large ℓ(B)·d): fast mode only
+        ex = want
+        paths[("exact-unsupported", fp)] = paths.get(("exact-unsupported", fp), 0) + 1
     fa = np.asarray(sk.linear_combination(basis, theta, pts)).reshape(want.shape)
     ok_exact = same(ex, want)
     with np.errstate(all="ignore"):

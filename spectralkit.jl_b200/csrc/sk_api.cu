@@ -504,6 +504,8 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         CK(skk::smolyak_block_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
+    if (!skk::smolyak_direct_fits(*plan, false))
+        SK_FAIL(SK_ERR_UNSUPPORTED, "basis too large for the bit-identical direct kernel: d * l(B) * (order + 1) doubles per point for 32 points exceed shared memory" "(fast mode serves such bases)");
     CK(skk::smolyak_direct_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
     return SK_OK;
 }
@@ -638,7 +640,10 @@ int sk_basis_at(const sk_plan *plan, const double *x, int64_t n, double *out, in
     const int d = uni ? 1 : plan->basis.d;
     auto run = [&](const double *dx, double *dout) -> int {
         if (uni) CK(skk::uni_basis_at(plan->basis.N, plan->tr[0], plan->order, dx, n, dout, ld, stream));
-        else CK(skk::smolyak_direct_basis_at(*plan, dx, n, dout, ld, stream));
+        else {
+            if (!skk::smolyak_direct_fits(*plan, true)) SK_FAIL(SK_ERR_UNSUPPORTED, "basis too large for the bit-identical direct kernel: d * l(B) * (order + 1) doubles per point for 32 points exceed shared memory" );
+            CK(skk::smolyak_direct_basis_at(*plan, dx, n, dout, ld, stream));
+        }
         return SK_OK;
     };
     if (flags & SK_MEM_DEVICE) return run(x, out);

@@ -458,6 +458,15 @@ static cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// The direct kernels keep every dimension's full Chebyshev table (d·ℓ(B)·(order + 1) doubles) per point in shared
+// memory, 32 points per CTA at least (one warp per named barrier): bases beyond that are refused up front (sk_api.cu).
+static constexpr size_t kDirectSmemLimit = 224 * 1024;
+bool smolyak_direct_fits(const sk_plan &plan, bool for_basis) {
+    const size_t tab_point = (size_t)plan.basis.d * (size_t)plan.H * plan_emax(plan) * sizeof(double);
+    const size_t extra = for_basis ? 3 * (size_t)plan.E * sizeof(double) : 0;
+    return (tab_point + extra) * 32 <= kDirectSmemLimit;
+}
+
 cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
                                    double *out, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
@@ -468,7 +477,7 @@ cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int
     size_t per_point = (size_t)q.d * q.H * emax * sizeof(double);
     // independent sums per point: components, or groups of 8 coefficient vectors
     const int lanes_wanted = nvec > 1 ? (nvec + 7) / 8 : (q.ncomp ? q.ncomp : 1);
-    int P = pick_points_per_block(per_point, 200 * 1024);
+    int P = pick_points_per_block(per_point, kDirectSmemLimit);
     if (!P) return cudaErrorInvalidConfiguration;
     if (lanes_wanted == 1 && n <= (int64_t)P * sm_count() / 2) while (P > 32 && n <= (int64_t)(P / 2) * sm_count()) P >>= 1;   // few points: more, smaller tiles
     int ny = std::max(1, std::min(lanes_wanted, 1024 / P));
@@ -503,7 +512,7 @@ cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_
     q.no_bulk = force >= 0 ? force : (q.E == 1);
     const int emax = plan_emax(plan);
     const size_t tab_point = (size_t)q.d * q.H * emax * sizeof(double);
-    const size_t limit = 200 * 1024;
+    const size_t limit = kDirectSmemLimit;
     int P = 0, ny = 1;
     // points per CTA: P = 64 (two warps per lane) with as many term lanes as fit (<= 8: 15 named barriers, 512+
     // threads); fall back to fewer points when the tables are large

@@ -14,6 +14,7 @@ cudaError_t uni_basis_at(int N, const sk_transform &tr, int order, const double 
                          int64_t ld, cudaStream_t stream);
 
 // ---- Smolyak, reference operation order (direct form, index table)
+bool smolyak_direct_fits(const sk_plan &plan, bool for_basis);      // tables of 32 points fit in shared memory
 cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n,
                                    double *out, cudaStream_t stream);
 cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld,

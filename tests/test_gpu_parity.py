@@ -254,6 +254,25 @@ def test_smolyak_exact_bit_identical(orc, code, d, B, M):
                     orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec))
 
 
+def test_smolyak_exact_mode_table_limit_is_reported(orc):
+    # the bit-identical direct kernels hold d·ℓ(B)·(order+1) doubles per point for 32 points in shared memory; a basis
+    # beyond that (InteriorGrid, B = 4: ℓ = 81, six dimensions, gradient) is refused with a clear error, not a CUDA
+    # launch failure, and the fast path still serves it within tolerance
+    code, d, B = 0, 6, 4
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    rng = np.random.default_rng(99)
+    theta = rng.standard_normal(sk.dimension(basis))
+    x = rand_pm1(rng, (50, d))
+    with pytest.raises(sk.UnsupportedError):
+        sk.linear_combination(basis, theta, sk.gradient(d)(x), exact=True)
+    ospec = orc.gradient_spec(d)
+    want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
+    scale = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec, absmode=True)
+    assert within(sk.linear_combination(basis, theta, sk.gradient(d)(x)), want, scale)
+    # values only need a third of the table: still bit-identical
+    assert same(sk.linear_combination(basis, theta, x, exact=True), orc.smolyak_lincomb(code, d, B, B, theta, x)[:, 0])
+
+
 @pytest.mark.parametrize("code", [0, 1, 2])
 @pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6])
 def test_smolyak_single_budget_leaf_kernels(orc, code, d):
