@@ -111,7 +111,11 @@ typedef struct sk_plan_info {
 #define SK_MEM_DEVICE 1u        /* x, theta, out are device pointers on the plan's device */
 #define SK_MODE_FAST 0u         /* FMA-contracted, nested evaluation; within the stated tolerance */
 #define SK_MODE_EXACT 2u        /* reference operation order, no contraction: bit-identical to the
-                                   reference restatement (sequential sum, mul-then-add) */
+                                   reference restatement (sequential sum, mul-then-add).  Smolyak
+                                   bases with d * l(B) * (max order + 1) > 896 (full Chebyshev
+                                   tables of 32 points exceed shared memory) return
+                                   SK_ERR_UNSUPPORTED in this mode and in sk_basis_at; SK_MODE_FAST
+                                   serves them */
 
 /* ---------------------------------------------------------------- library */
 const char *sk_version(void);
