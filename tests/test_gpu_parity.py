@@ -767,7 +767,7 @@ def test_stacked_coefficients_like_make_policy_functions(orc):
 
 
 def test_randomised_parity_sweep():
-    # profiles/fuzz_parity.py walks the whole dispatch table with random configurations (8 000 of them are logged in
+    # profiles/fuzz_parity.py walks the whole dispatch table with random configurations (20 000 of them are logged in
     # profiles/r1_fuzz_parity.jsonl); a short sweep runs with the suite
     import json
     import subprocess
