@@ -40,6 +40,7 @@ extern "C" {
 #define SK_MAX_BLOCKS 8      /* block cap M */
 #define SK_MAX_ORDER 5       /* univariate derivative order D (test/test_chebyshev.jl:93 uses 5) */
 #define SK_MAX_COMP 64       /* components of a ∂ specification */
+#define SK_MAX_TERMS (1 << 24) /* dimension(basis) of a Smolyak basis: tables are sized by it (SK_ERR_UNSUPPORTED above) */
 
 enum sk_status {
     SK_OK = 0,
@@ -195,15 +196,37 @@ int sk_collocation_solve(const sk_plan *plan, const double *y, int nrhs, double 
 /* ---------------------------------------------------------------- multi-GPU (one process, G devices) */
 /* Points are independent: contiguous slices of ceil(n/G) points per device, plans replicated,
  * θ copied to each device, no reduction, outputs land in the caller's host buffer.
- * plans[g] must live on distinct devices.  Host pointers only. */
+ * plans[g] must live on distinct devices.  Host pointers only.  (The reference is single-threaded; the
+ * caller-side loop this replaces is the broadcast of test/test_generic_api.jl:22.) */
 int sk_linear_combination_sharded(sk_plan *const *plans, int ngpu, const double *theta, int64_t theta_len,
                                   int nvec, const double *x, int64_t n, double *out, uint32_t flags);
+
+/* Device-resident shards (SURVEY.md §8(b) "sk_*_sharded(comm, …)", §8(e)).  A communicator is a single-process
+ * NCCL clique over `devices` (NCCL is bound at run time: SK_ERR_NCCL if libnccl.so.2 cannot be loaded or
+ * fails); it also owns one stream per device on which the calls below run. */
+typedef struct sk_comm sk_comm;  /* opaque */
+int sk_comm_create(int ngpu, const int *devices, sk_comm **out);
+int sk_comm_destroy(sk_comm *comm);
+int sk_comm_size(const sk_comm *comm, int *ngpu, int *nccl_version);
+/* C1: one broadcast of the coefficients from device `root` to theta_dev[g] on every device (count doubles). */
+int sk_broadcast_coefficients(sk_comm *comm, double *const *theta_dev, int64_t count, int root);
+/* linear_combination over device-resident slices: device g holds points [g·per, min(n, (g+1)·per)), per = ceil(n/G),
+ * in x_dev[g], and the coefficients in theta_dev[g]; plans[g] lives on the communicator's device g.
+ * gather == 0: out_dev[g] = that slice's results [slice][E] (outputs stay sharded: the default of SURVEY.md §8(e)).
+ * gather != 0 (C2): every out_dev[g] is a full buffer of per·G rows; device g writes its slice at row g·per and an
+ *   in-place ncclAllGather over NVLink completes all G copies (rows >= n are padding).
+ * ms_compute / ms_gather: optional [G] arrays, device-timed duration of the two phases per device.  Synchronises. */
+int sk_linear_combination_sharded_device(sk_comm *comm, sk_plan *const *plans, const double *const *theta_dev,
+                                         int64_t theta_len, int nvec, const double *const *x_dev, int64_t n,
+                                         double *const *out_dev, int gather, uint32_t flags, float *ms_compute,
+                                         float *ms_gather);
 
 /* ---------------------------------------------------------------- measurement helpers */
 /* Measures the FP64 pipe on `device`: which = 0 DFMA (CUDA-core), 1 DMMA (mma.sync m8n8k4 f64),
  * 2 both at once (half the warps each: shows whether they share one pipe), 3 DFMA with three distinct register
  * operands per instruction (the register-file-bound rate of code without operand reuse).
- * Runs for about `seconds`; returns TFLOP/s of the best (burst) and of the whole loop (sustained). */
+ * Runs for about `seconds`; returns TFLOP/s of the best single launch timed alone (burst) and of launches queued back to
+ * back between two events with no host synchronisation in between (sustained). */
 int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, double *tflops_sustained);
 /* Closed-form FP64 flop count per point of linear_combination with a K×nvec coefficient block (the DMMA kernel:
  * 2·K·nvec in the contraction + the generation of the collocation tile); nvec == 1: flops_per_point_fast. */

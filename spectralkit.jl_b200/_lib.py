@@ -31,6 +31,10 @@ class UnsupportedError(NotImplementedError):
     """`error("… not implemented yet")` / MethodError in the reference."""
 
 
+class NcclError(RuntimeError):
+    """NCCL could not be loaded or a collective failed (SK_ERR_NCCL)."""
+
+
 class CudaError(RuntimeError):
     """CUDA failure or no usable device: there is no CPU fallback."""
 
@@ -58,7 +62,8 @@ EXPORTS = ["sk_version", "sk_last_error", "sk_device_count", "sk_transform_make"
            "sk_nesting_block_length", "sk_grid_shuffle", "sk_dimension", "sk_parent_dimension", "sk_smolyak_indices",
            "sk_grid", "sk_partials_canonical", "sk_plan_create", "sk_plan_destroy", "sk_plan_get_info",
            "sk_linear_combination", "sk_basis_at", "sk_transform_to", "sk_transform_from",
-           "sk_linear_combination_sharded", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_fp64_peak", "sk_launch_count"]
+           "sk_linear_combination_sharded", "sk_comm_create", "sk_comm_destroy", "sk_comm_size", "sk_broadcast_coefficients",
+           "sk_linear_combination_sharded_device", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_fp64_peak", "sk_launch_count"]
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
@@ -86,6 +91,12 @@ lib.sk_basis_at.argtypes = [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_uint32, _vp
 lib.sk_transform_to.argtypes = [C.POINTER(Transform), C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_uint32, C.c_int, _vp]
 lib.sk_transform_from.argtypes = [C.POINTER(Transform), C.c_int, _vp, C.c_int64, _vp, C.c_uint32, C.c_int, _vp]
 lib.sk_linear_combination_sharded.argtypes = [C.POINTER(_vp), C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int64, _vp, C.c_uint32]
+lib.sk_comm_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
+lib.sk_comm_destroy.argtypes = [_vp]
+lib.sk_comm_size.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.sk_broadcast_coefficients.argtypes = [_vp, C.POINTER(_vp), C.c_int64, C.c_int]
+lib.sk_linear_combination_sharded_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.c_int64, C.c_int, C.POINTER(_vp), C.c_int64,
+                                                     C.POINTER(_vp), C.c_int, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
 lib.sk_is_subset_basis.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(C.c_int)]
 lib.sk_augment_coefficients.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), _vp, C.c_int64, C.c_int, _vp]
 lib.sk_coefficient_block_flops.argtypes = [_vp, C.c_int]
@@ -105,4 +116,6 @@ def check(rc: int) -> None:
         raise DomainError(msg)
     if rc == SK_ERR_UNSUPPORTED:
         raise UnsupportedError(msg)
+    if rc == SK_ERR_NCCL:
+        raise NcclError(msg)
     raise CudaError(f"status {rc}: {msg}")

@@ -69,6 +69,8 @@ int normalise_basis(const sk_basis_desc *in, sk_basis_desc *out) {
     out->M = in->M > in->B ? in->B : in->M;                                            // :15-16 (the shim warns)
     if (out->M > SK_MAX_BLOCKS) SK_FAIL(SK_ERR_UNSUPPORTED, "block cap M above SK_MAX_BLOCKS");
     if (skh::total_length(out->grid_kind, out->M) > 65535) SK_FAIL(SK_ERR_UNSUPPORTED, "parent dimension above 65535");
+    // tables are sized by K: refuse index sets beyond SK_MAX_TERMS up front (d = 16, B = M = 8, InteriorGrid would be 4.3e8)
+    if (skh::smolyak_count(out->grid_kind, out->d, out->B, out->M) > (int64_t)SK_MAX_TERMS) SK_FAIL(SK_ERR_UNSUPPORTED, "basis dimension above SK_MAX_TERMS");
     out->N = 0;
     return SK_OK;
 }
@@ -91,6 +93,24 @@ int check_transform(const sk_transform &t) {
 
 bool is_rational(const sk_transform &t) { return t.kind == SK_TR_SEMI_INF_RATIONAL || t.kind == SK_TR_INF_RATIONAL; }
 
+// ------------------------------------------------------------------------------ exception boundary
+// Nothing may unwind through the C ABI into ctypes or a Julia ccall: the entry points that build tables sized by the
+// basis run behind this guard and turn allocation failures into status codes.
+template <class F>
+int guarded(const char *what, F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        set_error(std::string(what) + ": out of host memory");
+        return SK_ERR_UNSUPPORTED;
+    } catch (const std::exception &e) {
+        set_error(std::string(what) + ": " + e.what());
+        return SK_ERR_ARGUMENT;
+    } catch (...) {
+        set_error(std::string(what) + ": unknown exception");
+        return SK_ERR_ARGUMENT;
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -169,7 +189,7 @@ int sk_parent_dimension(const sk_basis_desc *basis, int64_t *H) {
     return SK_OK;
 }
 
-int sk_smolyak_indices(const sk_basis_desc *basis, int32_t *out) {
+static int sk_smolyak_indices_impl(const sk_basis_desc *basis, int32_t *out) {
     sk_basis_desc b;
     int rc = normalise_basis(basis, &b);
     if (rc != SK_OK) return rc;
@@ -180,7 +200,7 @@ int sk_smolyak_indices(const sk_basis_desc *basis, int32_t *out) {
     return SK_OK;
 }
 
-int sk_grid(const sk_basis_desc *basis, const sk_transform *tr, double *out) {
+static int sk_grid_impl(const sk_basis_desc *basis, const sk_transform *tr, double *out) {
     sk_basis_desc b;
     int rc = normalise_basis(basis, &b);
     if (rc != SK_OK) return rc;
@@ -251,7 +271,7 @@ bool subset_basis(const sk_basis_desc &a, const sk_transform *ta, const sk_basis
 }
 }  // namespace
 
-int sk_is_subset_basis(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2, int *out) {
+static int sk_is_subset_basis_impl(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2, int *out) {
     sk_basis_desc a, b;
     int rc = normalise_basis(basis1, &a);
     if (rc != SK_OK) return rc;
@@ -262,7 +282,7 @@ int sk_is_subset_basis(const sk_basis_desc *basis1, const sk_transform *tr1, con
     return SK_OK;
 }
 
-int sk_augment_coefficients(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2,
+static int sk_augment_coefficients_impl(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2,
                             const double *theta1, int64_t theta1_len, int nvec, double *theta2) {
     sk_basis_desc a, b;
     int rc = normalise_basis(basis1, &a);
@@ -297,7 +317,7 @@ int sk_augment_coefficients(const sk_basis_desc *basis1, const sk_transform *tr1
 }
 
 // ------------------------------------------------------------------------------ plans
-int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_deriv_spec *spec, int device,
+static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *tr, const sk_deriv_spec *spec, int device,
                    sk_plan **out) {
     if (!out) SK_FAIL(SK_ERR_ARGUMENT, "out is NULL");
     *out = nullptr;
@@ -358,7 +378,9 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
         for (int j = 0; j < d; j++) ftab += (double)(p->H - 1) * (p->deg[j] == 0 ? 2 : p->deg[j] == 1 ? 6 : 12);
         p->flops_direct = (double)p->K * (C * (d - 1) + 2 * C) + ftab;
         p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
-        if (!p->fast_kernel && p->fast_mode < 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+        // any ∂ request no specialised kernel serves (general specifications; gradients with M < B or d > 10 that neither
+        // the leaf nor the run-program kernel takes) goes to the general nested kernel when its state fits
+        if (!p->fast_kernel && p->ncomp > 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
         // gradients the leaf kernel cannot serve (block cap M < B, θ too large): the generic nested kernel keeps its state
         // in registers, which spill beyond 8 dimensions (d = 10, B = 3: 3.6 vs 8.9 Mpoints/s); the general kernel keeps it
         // in shared memory
@@ -432,20 +454,35 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
     return SK_OK;
 }
 
+// ------------------------------------------------------------------------------ guarded entry points (see `guarded` above)
+int sk_smolyak_indices(const sk_basis_desc *basis, int32_t *out) { return guarded("sk_smolyak_indices", [&] { return sk_smolyak_indices_impl(basis, out); }); }
+int sk_grid(const sk_basis_desc *basis, const sk_transform *tr, double *out) { return guarded("sk_grid", [&] { return sk_grid_impl(basis, tr, out); }); }
+int sk_is_subset_basis(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2, int *out) {
+    return guarded("sk_is_subset_basis", [&] { return sk_is_subset_basis_impl(basis1, tr1, basis2, tr2, out); });
+}
+int sk_augment_coefficients(const sk_basis_desc *basis1, const sk_transform *tr1, const sk_basis_desc *basis2, const sk_transform *tr2,
+                            const double *theta1, int64_t theta1_len, int nvec, double *theta2) {
+    return guarded("sk_augment_coefficients", [&] { return sk_augment_coefficients_impl(basis1, tr1, basis2, tr2, theta1, theta1_len, nvec, theta2); });
+}
+int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_deriv_spec *spec, int device, sk_plan **out) {
+    return guarded("sk_plan_create", [&] { return sk_plan_create_impl(basis, tr, spec, device, out); });
+}
+
+// frees everything the plan owns on its device; also runs when sk_plan_create fails half-way (unique_ptr)
+sk_plan::~sk_plan() {
+    DeviceGuard g(device);
+    if (d_idx) cudaFree(d_idx);
+    if (d_runs) cudaFree(d_runs);
+    if (d_units) cudaFree(d_units);
+    if (d_thmap) cudaFree(d_thmap);
+    if (d_fac) cudaFree(d_fac);
+    if (d_tree) cudaFree(d_tree);
+    if (d_bprog) cudaFree(d_bprog);
+    for (sk_workspace *w : ws_free) workspace_destroy(w);
+    ws_free.clear();
+}
+
 int sk_plan_destroy(sk_plan *plan) {
-    if (!plan) return SK_OK;
-    {
-        DeviceGuard g(plan->device);
-        if (plan->d_idx) cudaFree(plan->d_idx);
-        if (plan->d_runs) cudaFree(plan->d_runs);
-        if (plan->d_units) cudaFree(plan->d_units);
-        if (plan->d_thmap) cudaFree(plan->d_thmap);
-        if (plan->d_fac) cudaFree(plan->d_fac);
-        if (plan->d_tree) cudaFree(plan->d_tree);
-        for (sk_workspace *w : plan->ws_free) workspace_destroy(w);
-        plan->ws_free.clear();
-        if (plan->d_bprog) cudaFree(plan->d_bprog);
-    }
     delete plan;
     return SK_OK;
 }
@@ -524,8 +561,14 @@ struct WorkspaceLease {
         std::lock_guard<std::mutex> lk(plan->ws_mu);
         if (!plan->ws_free.empty()) { ws = plan->ws_free.back(); plan->ws_free.pop_back(); }
     }
+    bool poisoned = false;      // a failed call may leave copies or kernels in flight on the workspace's streams
     ~WorkspaceLease() {
         if (!ws) return;
+        if (poisoned) {        // drain and destroy instead of handing half-used streams and buffers to the next call
+            for (int i = 0; i < 3; i++) if (ws->s[i]) cudaStreamSynchronize((cudaStream_t)ws->s[i]);
+            workspace_destroy(ws);
+            return;
+        }
         std::unique_lock<std::mutex> lk(plan->ws_mu);
         if (plan->ws_free.size() < 2) { plan->ws_free.push_back(ws); return; }
         lk.unlock();
@@ -593,6 +636,7 @@ int sk_linear_combination(const sk_plan *plan, const double *theta, int64_t thet
     const size_t theta_bytes = (size_t)plan->K * nvec * sizeof(double);
     const int64_t chunk = std::min<int64_t>(n, host_chunk_points());
     WorkspaceLease lease(plan);
+    lease.poisoned = true;      // cleared when the call completes: every early return below drains and drops the workspace
     rc = lease.ensure(theta_bytes, (size_t)chunk * d * sizeof(double), (size_t)chunk * Eout * sizeof(double));
     if (rc != SK_OK) return rc;
     sk_workspace &w = *lease.ws;
@@ -625,6 +669,7 @@ int sk_linear_combination(const sk_plan *plan, const double *theta, int64_t thet
     CK(cudaStreamSynchronize(s_out));
     CK(cudaStreamSynchronize(s_k));
     CK(cudaStreamSynchronize(s_in));
+    lease.poisoned = false;
     return SK_OK;
 }
 
@@ -762,9 +807,10 @@ int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, do
     double flops = 0, best = 0;
     for (int w = 0; w < 3; w++) CK(skk::fp64_peak_launch(which, iters, sink, &flops, nullptr));
     CK(cudaDeviceSynchronize());
+    // burst: the best single launch, timed alone (half of the budget)
     CK(cudaEventRecord(t0, nullptr));
     int launches = 0;
-    float total_ms = 0;
+    float total_ms = 0, best_ms = 1e30f;
     do {
         CK(cudaEventRecord(e0, nullptr));
         CK(skk::fp64_peak_launch(which, iters, sink, &flops, nullptr));
@@ -773,13 +819,21 @@ int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, do
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         best = std::max(best, flops / (ms * 1e-3));
+        best_ms = std::min(best_ms, ms);
         launches++;
         CK(cudaEventRecord(t1, nullptr));
         CK(cudaEventSynchronize(t1));
         CK(cudaEventElapsedTime(&total_ms, t0, t1));
-    } while (total_ms < seconds * 1e3 && launches < 100000);
+    } while (total_ms < seconds * 0.5e3 && launches < 100000);
+    // sustained: launches queued back to back between two events, no host synchronisation in between
+    const int queued = (int)std::min(20000.0, std::max(8.0, seconds * 0.5e3 / best_ms));
+    CK(cudaEventRecord(t0, nullptr));
+    for (int i = 0; i < queued; i++) CK(skk::fp64_peak_launch(which, iters, sink, &flops, nullptr));
+    CK(cudaEventRecord(t1, nullptr));
+    CK(cudaEventSynchronize(t1));
+    CK(cudaEventElapsedTime(&total_ms, t0, t1));
     *tflops_burst = best * 1e-12;
-    *tflops_sustained = flops * launches / (total_ms * 1e-3) * 1e-12;
+    *tflops_sustained = flops * queued / (total_ms * 1e-3) * 1e-12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
     cudaFree(sink);
     return SK_OK;

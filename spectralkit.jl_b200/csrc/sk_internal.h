@@ -98,4 +98,8 @@ struct sk_plan {
     // host-buffer staging pool (the only mutable state of a plan; guarded by ws_mu)
     mutable std::mutex ws_mu;
     mutable std::vector<sk_workspace *> ws_free;
+    sk_plan() = default;
+    sk_plan(const sk_plan &) = delete;
+    sk_plan &operator=(const sk_plan &) = delete;
+    ~sk_plan();                  // frees the device tables and the staging pool (csrc/sk_api.cu)
 };

@@ -151,6 +151,14 @@ __global__ void __launch_bounds__(256) uni_lincomb_nvec_kernel(int N, sk_transfo
     }
 }
 
+// bookkeeping of the two constant-bank coefficient slots (c_uni_theta), shared by all launch_uni<DP1> instantiations
+struct UniConstSlots {
+    std::mutex mu;
+    cudaEvent_t done[64][2] = {};      // per device and slot: recorded after the last kernel that reads the slot
+    unsigned next[64] = {};
+};
+static UniConstSlots &uni_const_slots() { static UniConstSlots s; return s; }
+
 template <int DP1>
 static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const double *theta, const double *x, int64_t n,
                               double *out, cudaStream_t stream) {
@@ -165,11 +173,12 @@ static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const d
     cudaGetDevice(&dev);
     // (small batches stay on the shared-memory path: the symbol copy and the slot event cost ≈ 10 µs of launch latency)
     if (!exact && use_const && N <= kUniConstMax && dev < 64 && n >= ((int64_t)1 << 17)) {
-        static std::mutex mu;
-        static cudaEvent_t done[64][2] = {};
-        static unsigned next[64] = {};
-        std::lock_guard<std::mutex> lk(mu);
-        const int slot = (int)(next[dev]++ & 1u);
+        // ONE set of slot bookkeeping per device for every derivative order: all instantiations of this template write
+        // the same __constant__ array, so the slot counter and the "last reader" events must be shared between them
+        UniConstSlots &cs = uni_const_slots();
+        std::lock_guard<std::mutex> lk(cs.mu);
+        cudaEvent_t (&done)[64][2] = cs.done;
+        const int slot = (int)(cs.next[dev]++ & 1u);
         cudaError_t e = cudaSuccess;
         if (!done[dev][slot]) e = cudaEventCreateWithFlags(&done[dev][slot], cudaEventDisableTiming);
         else e = cudaStreamWaitEvent(stream, done[dev][slot], 0);       // the launch that last read this slot

@@ -1,10 +1,16 @@
-"""Multi-GPU plumbing: one process per GPU, points sharded, θ broadcast once,
-outputs gathered only on request.  torch.distributed is the transport (NCCL on GPUs, gloo in the CPU
-tests); there is no reduction anywhere on this path, so nothing here touches the kernels.
+"""Multi-GPU plumbing: points sharded, θ broadcast once, outputs gathered only on request.
+
+Two deployment shapes, same slicing rule (contiguous slices of ceil(n/G) points):
+  * one process per GPU (torchrun): `torch.distributed` is the transport (NCCL on GPUs, gloo in the CPU tests):
+    `broadcast_coefficients`, `gather_outputs`;
+  * one process, G devices: the library's own communicator (`Comm`, C ABI `sk_comm_*`) with the device-pointer
+    entry `sk_linear_combination_sharded_device` and its in-library NCCL all-gather.
+There is no reduction anywhere on this path, so nothing here touches the kernels.
 """
 from __future__ import annotations
 
-from typing import Tuple
+import ctypes as C
+from typing import Sequence, Tuple
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -25,17 +31,84 @@ def broadcast_coefficients(theta, src: int = 0):
     return theta
 
 
-def gather_outputs(out_local, n_total: int):
-    """C2 (only when the caller wants a device-resident full output): all-gather of the per-rank
-    result slices, padded to the common slice length and trimmed to n_total rows."""
+def gather_outputs(out_local, n_total: int, full=None):
+    """C2 (only when the caller wants a device-resident full output): all-gather of the per-rank result slices.
+
+    The slices are the `shard_bounds` slices, so all but the trailing ones have ceil(n/world) rows; the collective
+    runs in place on one padded buffer (`all_gather_into_tensor`: a single ncclAllGather, no concatenation copy) and
+    the result is the first n_total rows of it.  `full` may be a preallocated (ceil(n/world)·world, …) buffer."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return out_local
-    world = dist.get_world_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
     per = (n_total + world - 1) // world
-    pad = torch.zeros((per,) + tuple(out_local.shape[1:]), dtype=out_local.dtype, device=out_local.device)
-    pad[: out_local.shape[0]] = out_local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
-    return torch.cat(parts, 0)[:n_total]
+    tail = tuple(out_local.shape[1:])
+    if full is None:
+        full = torch.empty((per * world,) + tail, dtype=out_local.dtype, device=out_local.device)
+    mine = full[rank * per:(rank + 1) * per]
+    if out_local.data_ptr() != mine.data_ptr():
+        mine[: out_local.shape[0]].copy_(out_local)
+    if out_local.shape[0] < per:
+        mine[out_local.shape[0]:].zero_()
+    try:
+        dist.all_gather_into_tensor(full, mine)
+    except (RuntimeError, NotImplementedError):      # backends without the flat collective (old gloo)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous())
+        full = torch.cat(parts, 0)
+    return full[:n_total]
+
+
+class Comm:
+    """Single-process NCCL clique over `devices` (C ABI `sk_comm_create`)."""
+
+    def __init__(self, devices: Sequence[int]):
+        from . import _lib as L
+        self._L = L
+        self.devices = [int(g) for g in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        L.check(L.lib.sk_comm_create(len(self.devices), arr, C.byref(h)))
+        self.handle = h
+
+    @property
+    def nccl_version(self) -> int:
+        n, v = C.c_int(0), C.c_int(0)
+        self._L.check(self._L.lib.sk_comm_size(self.handle, C.byref(n), C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.handle:
+            self._L.lib.sk_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def broadcast_coefficients(self, thetas, root: int = 0):
+        """thetas[g]: a float64 CUDA tensor on devices[g]; the root's content is copied to all of them."""
+        L = self._L
+        ptrs = (C.c_void_p * len(thetas))(*[int(t.data_ptr()) for t in thetas])
+        L.check(L.lib.sk_broadcast_coefficients(self.handle, ptrs, int(thetas[0].numel()), int(root)))
+        return thetas
+
+    def linear_combination(self, plans, thetas, xs, n_total: int, outs, *, nvec: int = 1, gather: bool = False, exact: bool = False):
+        """Device-resident sharded evaluation (`sk_linear_combination_sharded_device`).  plans[g] / thetas[g] / xs[g] /
+        outs[g] live on devices[g]; xs[g] is the g-th `shard_bounds` slice; with gather=True every outs[g] is a full
+        (ceil(n/G)·G, E) buffer.  Returns (ms_compute[g], ms_gather[g]) device-timed per device."""
+        L = self._L
+        G = len(self.devices)
+        hp = (C.c_void_p * G)(*[p.handle for p in plans])
+        tp = (C.c_void_p * G)(*[int(t.data_ptr()) for t in thetas])
+        xp = (C.c_void_p * G)(*[int(x.data_ptr()) for x in xs])
+        op = (C.c_void_p * G)(*[int(o.data_ptr()) for o in outs])
+        msc, msg = (C.c_float * G)(), (C.c_float * G)()
+        theta_len = int(thetas[0].shape[0])
+        flags = L.SK_MEM_DEVICE | (L.SK_MODE_EXACT if exact else L.SK_MODE_FAST)
+        L.check(L.lib.sk_linear_combination_sharded_device(self.handle, hp, tp, theta_len, int(nvec), xp, int(n_total), op,
+                                                           1 if gather else 0, flags, msc, msg))
+        return list(msc), list(msg)
