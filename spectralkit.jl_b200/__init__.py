@@ -12,6 +12,6 @@ Layout
 from .api import *  # noqa: F401,F403
 from .api import d, get_plan, fp64_peak, launch_count, smolyak_indices, grid_shuffle  # noqa: F401
 from . import _lib  # noqa: F401
-from .sharding import shard_bounds, broadcast_coefficients, gather_outputs  # noqa: F401
+from .sharding import shard_bounds, broadcast_coefficients, gather_outputs, Comm  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]
