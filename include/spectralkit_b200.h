@@ -112,11 +112,12 @@ typedef struct sk_plan_info {
 #define SK_MEM_DEVICE 1u        /* x, theta, out are device pointers on the plan's device */
 #define SK_MODE_FAST 0u         /* FMA-contracted, nested evaluation; within the stated tolerance */
 #define SK_MODE_EXACT 2u        /* reference operation order, no contraction: bit-identical to the
-                                   reference restatement (sequential sum, mul-then-add).  Smolyak
-                                   bases with d * l(B) * (max order + 1) > 896 (full Chebyshev
-                                   tables of 32 points exceed shared memory) return
-                                   SK_ERR_UNSUPPORTED in this mode and in sk_basis_at; SK_MODE_FAST
-                                   serves them */
+                                   reference restatement (sequential sum, mul-then-add).  For
+                                   sk_linear_combination this mode keeps every dimension's full table
+                                   on chip: Smolyak bases with d * l(B) * (max order + 1) > 896 return
+                                   SK_ERR_UNSUPPORTED there (SK_MODE_FAST serves them).  sk_basis_at /
+                                   collocation matrices are always bit-identical and have no such
+                                   limit (tables are streamed chunk by chunk, csrc/sk_basis.cu) */
 
 /* ---------------------------------------------------------------- library */
 const char *sk_version(void);
@@ -173,8 +174,9 @@ int sk_plan_get_info(const sk_plan *plan, sk_plan_info *info);
 int sk_linear_combination(const sk_plan *plan, const double *theta, int64_t theta_len, int nvec,
                           const double *x, int64_t n, double *out, uint32_t flags, void *stream);
 /* collocation_matrix(basis, x) == basis_at at n points (generic_api.jl:217-227); always in the
- * reference's operation order (bit-identical basis values).  ld = leading dimension in elements
- * (>= n). */
+ * reference's operation order (bit-identical basis values), for any basis and any ∂ request.  ld = leading
+ * dimension in elements (>= n); only the first n entries of every column are written.  Host buffers are
+ * streamed in chunks of points (the full matrix never has to fit on the device in one piece). */
 int sk_basis_at(const sk_plan *plan, const double *x, int64_t n, double *out, int64_t ld,
                 uint32_t flags, void *stream);
 /* transform_to / transform_from over n points of d coordinates (transformations.jl:112-139,

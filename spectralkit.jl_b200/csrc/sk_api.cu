@@ -471,6 +471,7 @@ int sk_plan_create(const sk_basis_desc *basis, const sk_transform *tr, const sk_
 // frees everything the plan owns on its device; also runs when sk_plan_create fails half-way (unique_ptr)
 sk_plan::~sk_plan() {
     DeviceGuard g(device);
+    skk::smolyak_tile_basis_forget(this);
     if (d_idx) cudaFree(d_idx);
     if (d_runs) cudaFree(d_runs);
     if (d_units) cudaFree(d_units);
@@ -683,30 +684,57 @@ int sk_basis_at(const sk_plan *plan, const double *x, int64_t n, double *out, in
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool uni = plan->basis.kind == SK_BASIS_CHEBYSHEV;
     const int d = uni ? 1 : plan->basis.d;
-    auto run = [&](const double *dx, double *dout) -> int {
-        if (uni) CK(skk::uni_basis_at(plan->basis.N, plan->tr[0], plan->order, dx, n, dout, ld, stream));
+    auto run = [&](const double *dx, double *dout, int64_t nn, int64_t ldd) -> int {
+        if (uni) CK(skk::uni_basis_at(plan->basis.N, plan->tr[0], plan->order, dx, nn, dout, ldd, stream));
         else {
-            if (!skk::smolyak_direct_fits(*plan, true)) SK_FAIL(SK_ERR_UNSUPPORTED, "basis too large for the bit-identical direct kernel: d * l(B) * (order + 1) doubles per point for 32 points exceed shared memory" );
-            CK(skk::smolyak_direct_basis_at(*plan, dx, n, dout, ld, stream));
+            static const int old_kernel = [] { const char *e = getenv("SK_BASIS_OLD"); return e ? atoi(e) : 0; }();   // A/B against the round-1 kernel
+            if (old_kernel && skk::smolyak_direct_fits(*plan, true)) CK(skk::smolyak_direct_basis_at(*plan, dx, nn, dout, ldd, stream));
+            else CK(skk::smolyak_tile_basis_at(*plan, dx, nn, dout, ldd, stream));
         }
         return SK_OK;
     };
-    if (flags & SK_MEM_DEVICE) return run(x, out);
-    const size_t xin = (size_t)n * d * sizeof(double);
-    const size_t oby = (size_t)ld * plan->K * plan->E * sizeof(double);
-    double *dx = nullptr, *dout = nullptr;
-    CK(cudaMalloc(&dx, xin));
-    cudaError_t e = cudaMalloc(&dout, oby);
-    if (e != cudaSuccess) { cudaFree(dx); CK(e); }
-    int rc = SK_OK;
-    e = cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && ld != n) e = cudaMemsetAsync(dout, 0, oby, stream);
-    if (e == cudaSuccess) rc = run(dx, dout);
-    if (e == cudaSuccess && rc == SK_OK) e = cudaMemcpyAsync(out, dout, oby, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && rc == SK_OK) e = cudaStreamSynchronize(stream);
-    cudaFree(dx); cudaFree(dout);
+    if (flags & SK_MEM_DEVICE) return run(x, out, n, ld);
+    // host buffers: points in chunks through the plan's staging workspace (the same 3-deep pipeline as
+    // sk_linear_combination): chunk i+1 is copied in and chunk i-1 copied out (one strided 2-D copy into the caller's
+    // column-major matrix) while chunk i is evaluated.  A 10^6 × 2 561 matrix never exists on the device in one piece.
+    const size_t col_bytes = (size_t)plan->K * plan->E * sizeof(double);          // bytes of one point's K elements
+    int64_t chunk = (int64_t)(((size_t)128 << 20) / col_bytes) & ~(int64_t)31;    // about 128 MB of results per chunk, whole 32-point tiles
+    chunk = std::max<int64_t>(32, std::min<int64_t>(chunk, n));
+    WorkspaceLease lease(plan);
+    lease.poisoned = true;
+    int rc = lease.ensure(0, (size_t)chunk * d * sizeof(double), (size_t)chunk * col_bytes);
     if (rc != SK_OK) return rc;
-    CK(e);
+    sk_workspace &w = *lease.ws;
+    constexpr int NB = sk_workspace::NBUF;
+    cudaStream_t s_in = (cudaStream_t)w.s[0], s_k = (cudaStream_t)w.s[1], s_out = (cudaStream_t)w.s[2];
+    CK(cudaEventRecord((cudaEvent_t)w.e0, stream));
+    CK(cudaStreamWaitEvent(s_in, (cudaEvent_t)w.e0, 0));
+    CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.e0, 0));
+    int64_t done_pts = 0;
+    for (int it = 0; done_pts < n; it++) {
+        const int bi = it % NB;
+        const int64_t m = std::min<int64_t>(chunk, n - done_pts);
+        if (it >= NB) {
+            CK(cudaStreamWaitEvent(s_in, (cudaEvent_t)w.done[bi], 0));
+            CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.outc[bi], 0));
+        }
+        CK(cudaMemcpyAsync(w.xb[bi], x + (size_t)done_pts * d, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        CK(cudaEventRecord((cudaEvent_t)w.in[bi], s_in));
+        CK(cudaStreamWaitEvent(s_k, (cudaEvent_t)w.in[bi], 0));
+        stream = s_k;
+        rc = run((const double *)w.xb[bi], (double *)w.ob[bi], m, m);      // device chunk: leading dimension m
+        if (rc != SK_OK) return rc;
+        CK(cudaEventRecord((cudaEvent_t)w.done[bi], s_k));
+        CK(cudaStreamWaitEvent(s_out, (cudaEvent_t)w.done[bi], 0));
+        CK(cudaMemcpy2DAsync(out + (size_t)done_pts * plan->E, (size_t)ld * plan->E * sizeof(double), w.ob[bi], (size_t)m * plan->E * sizeof(double),
+                             (size_t)m * plan->E * sizeof(double), (size_t)plan->K, cudaMemcpyDeviceToHost, s_out));
+        CK(cudaEventRecord((cudaEvent_t)w.outc[bi], s_out));
+        done_pts += m;
+    }
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaStreamSynchronize(s_k));
+    CK(cudaStreamSynchronize(s_in));
+    lease.poisoned = false;
     return SK_OK;
 }
 

@@ -20,6 +20,10 @@ cudaError_t smolyak_direct_lincomb(const sk_plan &plan, const double *theta, int
 cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld,
                                     cudaStream_t stream);
 
+// ---- Smolyak basis_at / collocation_matrix: chunked tables, TMA tensor-map stores (sk_basis.cu); any basis, any ∂ request
+cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld, cudaStream_t stream);
+void smolyak_tile_basis_forget(const sk_plan *plan);
+
 // ---- Smolyak, nested run-structured evaluation (values, or value + full gradient)
 bool smolyak_nested_supported(const sk_plan &plan);
 cudaError_t smolyak_nested_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n,

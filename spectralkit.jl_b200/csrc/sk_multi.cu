@@ -195,7 +195,7 @@ int sk_linear_combination_sharded_device(sk_comm *c, sk_plan *const *plans, cons
         if (g == 0) i0 = ig;
         else if (ig.K != i0.K || ig.E != i0.E || ig.d != i0.d) SK_FAIL(SK_ERR_ARGUMENT, "plans must describe the same basis");
     }
-    const int d = i0.d, Eout = nvec > 1 ? nvec : i0.E;
+    const int Eout = nvec > 1 ? nvec : i0.E;
     const int64_t per = (n + G - 1) / G;
     std::vector<int> rcs((size_t)G, SK_OK);
     std::vector<std::string> msgs((size_t)G);

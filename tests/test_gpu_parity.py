@@ -382,6 +382,47 @@ def test_smolyak_basis_at_bit_identical(orc, n):
         assert got.shape == (n, K, d + 1) and same(got, want.transpose(1, 0, 2))
 
 
+def test_smolyak_basis_at_large_tables_bit_identical(orc):
+    """Bases whose full Chebyshev tables exceeded the round-1 kernel's shared memory (d·ℓ(B)·(order+1) > 896): the
+    chunked-table kernel has no such limit (generic_api.jl:217-227 has none either).  InteriorGrid d=6 B=4 with a
+    gradient (ℓ = 81: 972 doubles per point), InteriorGrid2 d=10 B=3 gradient, a general ∂ spec with order 2, and a
+    leading dimension larger than n through the raw C ABI."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(77)
+    for code, d, B, n in [(0, 6, 4, 37), (2, 10, 3, 70), (0, 3, 5, 33)]:
+        basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+        K = sk.dimension(basis)
+        x = rand_pm1(rng, (n, d))
+        want = orc.smolyak_basis_at(code, d, B, B, x)
+        assert same(np.asarray(sk.basis_at(basis, x)), want[:, :, 0].T)
+        want = orc.smolyak_basis_at(code, d, B, B, x, spec=orc.gradient_spec(d))
+        got = np.asarray(sk.basis_at(basis, sk.gradient(d)(x)))
+        assert got.shape == (n, K, d + 1) and same(got, want.transpose(1, 0, 2))
+    # general specification with second order: ∂(2) ∪ ∂(0,1,1) in d = 3
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), 3)
+    spec = sk.partial(2) | sk.partial(0, 1, 1)
+    x = rand_pm1(rng, (45, 3))
+    table, _ = spec.expansion(3)
+    want = orc.smolyak_basis_at(2, 3, 4, 4, x, spec=np.asarray(table, dtype=np.int32))
+    got = np.asarray(sk.basis_at(basis, spec(x)))
+    assert same(got, want.transpose(1, 0, 2))
+    # ld > n (odd pitch: the tensor map cannot express it, plain stores) and ld > n with an even pitch (TMA)
+    L = sk._lib
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 4)
+    K = sk.dimension(basis)
+    plan = sk.get_plan(basis, 0, None, 0)
+    x = rand_pm1(rng, (50, 4))
+    want = orc.smolyak_basis_at(2, 4, 3, 3, x)[:, :, 0]                                 # (K, n)
+    xd = torch.as_tensor(x).cuda()
+    for ld in (53, 64):
+        out = torch.full((K, ld), -7.0, dtype=torch.float64, device="cuda")
+        L.check(L.lib.sk_basis_at(plan.handle, C.c_void_p(xd.data_ptr()), 50, C.c_void_p(out.data_ptr()), ld, L.SK_MEM_DEVICE, None))
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        assert same(o[:, :50], want) and (o[:, 50:] == -7.0).all()
+
+
 def test_smolyak_collocation_at_own_grid(orc):
     basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 3)
     Cm = sk.collocation_matrix(basis)
