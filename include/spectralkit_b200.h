@@ -190,10 +190,32 @@ int sk_transform_from(const sk_transform *tr, int d, const double *x, int64_t n,
 /* ---------------------------------------------------------------- fitting (initialisation time) */
 /* θ = collocation_matrix(basis) \ y on the basis' own grid (docs/src/index.md:92, test/test_smolyak.jl:20-21,
  * test/test_generic_api.jl:20).  The collocation matrix is generated on the device by the basis_at kernels; the
- * dense LU (partial pivoting, as Julia's `\` on a square matrix) is cuSOLVER's, loaded on first use.  The plan must
- * carry no derivative request.  y and theta: [K][nrhs], nrhs fastest (the layout of Vector{SVector{nrhs}}; nrhs = 1
+ * dense LU with partial pivoting (what Julia's `\` does on a square matrix) and the triangular solves are the library's
+ * own kernels (blocked right-looking factorisation, trailing updates on the FP64 tensor path; csrc/sk_solve.cu).  The
+ * plan must carry no derivative request; nrhs <= 96.  y and theta: [K][nrhs], nrhs fastest (the layout of Vector{SVector{nrhs}}; nrhs = 1
  * is a plain vector).  SK_ERR_ARGUMENT if the matrix is singular (Julia: SingularException).  Synchronises `stream`. */
 int sk_collocation_solve(const sk_plan *plan, const double *y, int nrhs, double *theta, uint32_t flags, void *stream);
+
+/* ---------------------------------------------------------------- Experimental: policy functions and residual sums */
+/* bridge(outer, inner) (src/experimental.jl:242-266): x ↦ transform_from(PM1, outer, transform_to(PM1, inner, x));
+ * kind SK_TR_NONE on both sides is the identity. */
+typedef struct sk_bridge {
+    sk_transform outer, inner;
+} sk_bridge;
+/* make_policy_functions (src/experimental.jl:156-166) evaluated for n points in one pass: policy m is
+ * bridges[m] ∘ linear_combination(basis, coefficients[m·K : (m+1)·K]) with K = dimension(basis); the stacked vector
+ * becomes the K×npol coefficient block of the hot path.  out[n][npol].  bridges == NULL: no transformation.
+ * SK_ERR_ARGUMENT unless coefficients_len == K·npol (the reference's @argcheck).  1 <= npol <= 64.  Synchronises. */
+int sk_policy_functions(const sk_plan *plan, const double *coefficients, int64_t coefficients_len, int npol,
+                        const sk_bridge *bridges, const double *x, int64_t n, double *out, uint32_t flags, void *stream);
+/* sum_abs2 reduced over a residual array (src/experimental.jl:218-233): Σ r², fixed partition and fixed reduction tree
+ * (reproducible; the reference adds left to right, so the last bits may differ).  r: host or device by flags. */
+int sk_sum_abs2(const double *r, int64_t count, double *result_host, uint32_t flags, int device, void *stream);
+/* The least-squares special case fused end to end: Σ_{i,m} (policy_m(x_i) − target[i][m])² without materialising the
+ * policy values or the residuals on the host. */
+int sk_policy_residual_ssq(const sk_plan *plan, const double *coefficients, int64_t coefficients_len, int npol,
+                           const sk_bridge *bridges, const double *x, int64_t n, const double *target,
+                           double *result_host, uint32_t flags, void *stream);
 
 /* ---------------------------------------------------------------- multi-GPU (one process, G devices) */
 /* Points are independent: contiguous slices of ceil(n/G) points per device, plans replicated,
@@ -233,6 +255,9 @@ int sk_fp64_peak(int device, int which, double seconds, double *tflops_burst, do
 /* Closed-form FP64 flop count per point of linear_combination with a K×nvec coefficient block (the DMMA kernel:
  * 2·K·nvec in the contraction + the generation of the collocation tile); nvec == 1: flops_per_point_fast. */
 double sk_coefficient_block_flops(const sk_plan *plan, int nvec);
+/* Times the library's LU factorisation on a K×K column-major device matrix (overwritten): mean device milliseconds over
+ * `reps` runs, (2/3)·K³ flop / time in TFLOP/s, and the milliseconds spent in the DMMA trailing updates alone. */
+int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, double *tflops, double *ms_gemm);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sk_launch_count(void);
 

@@ -12,6 +12,8 @@ Layout
 from .api import *  # noqa: F401,F403
 from .api import d, get_plan, fp64_peak, launch_count, smolyak_indices, grid_shuffle  # noqa: F401
 from . import _lib  # noqa: F401
+from . import experimental  # noqa: F401
+from .experimental import bridge, make_policy_functions, sum_of_squared_residuals, sum_abs2  # noqa: F401
 from .sharding import shard_bounds, broadcast_coefficients, gather_outputs, Comm  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

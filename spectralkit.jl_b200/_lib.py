@@ -51,6 +51,10 @@ class DerivSpec(C.Structure):
     _fields_ = [("order", C.c_int32), ("ncomp", C.c_int32), ("orders", C.POINTER(C.c_int32)), ("allow_rational_d2", C.c_int32)]
 
 
+class Bridge(C.Structure):
+    _fields_ = [("outer", Transform), ("inner", Transform)]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [("kind", C.c_int32), ("grid_kind", C.c_int32), ("d", C.c_int32), ("B", C.c_int32), ("M", C.c_int32), ("device", C.c_int32),
                 ("K", C.c_int64), ("H", C.c_int64), ("E", C.c_int32), ("fast_path", C.c_int32), ("n_runs", C.c_int64),
@@ -63,7 +67,8 @@ EXPORTS = ["sk_version", "sk_last_error", "sk_device_count", "sk_transform_make"
            "sk_grid", "sk_partials_canonical", "sk_plan_create", "sk_plan_destroy", "sk_plan_get_info",
            "sk_linear_combination", "sk_basis_at", "sk_transform_to", "sk_transform_from",
            "sk_linear_combination_sharded", "sk_comm_create", "sk_comm_destroy", "sk_comm_size", "sk_broadcast_coefficients",
-           "sk_linear_combination_sharded_device", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_fp64_peak", "sk_launch_count"]
+           "sk_linear_combination_sharded_device", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_policy_functions", "sk_sum_abs2", "sk_policy_residual_ssq",
+           "sk_fp64_peak", "sk_lu_benchmark", "sk_launch_count"]
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
@@ -103,6 +108,10 @@ lib.sk_coefficient_block_flops.argtypes = [_vp, C.c_int]
 lib.sk_coefficient_block_flops.restype = C.c_double
 lib.sk_collocation_solve.argtypes = [_vp, _vp, C.c_int, _vp, C.c_uint32, _vp]
 lib.sk_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp]
+lib.sk_lu_benchmark.argtypes = [_vp, C.c_int64, C.c_int, _dp, _dp, _dp]
+lib.sk_policy_functions.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_uint32, _vp]
+lib.sk_sum_abs2.argtypes = [_vp, C.c_int64, _dp, C.c_uint32, C.c_int, _vp]
+lib.sk_policy_residual_ssq.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int64, _vp, _dp, C.c_uint32, _vp]
 lib.sk_launch_count.restype = C.c_int64
 
 

@@ -1,14 +1,23 @@
 // SURVEY.md §8(f) rank 1 — the step before evaluation in every workflow: fitting θ on the basis' own grid,
 //     θ = collocation_matrix(basis) \ y        (docs/src/index.md:92, test/test_smolyak.jl:20-21,
 //                                               test/test_generic_api.jl:20)
-// The collocation matrix is generated on the device by the library's own basis_at kernels (bit-identical to
-// the reference's values) and never leaves it; the dense LU factorisation and the triangular solves — an
-// initialisation-time step, not on the hot path — are cuSOLVER's (getrf/getrs, partial pivoting like Julia's
-// `\` on a square matrix), loaded lazily with dlopen so that evaluation-only users never map the library.
-#include <dlfcn.h>
-
+// The collocation matrix is generated on the device by the library's own basis_at kernels (bit-identical to the
+// reference's values) and never leaves it.  Julia's `\` on a square dense matrix is an LU factorisation with partial
+// pivoting followed by two triangular solves; this file does the same with its own kernels (no cuSOLVER, no cuBLAS):
+//
+//   blocked right-looking LU, panels of NB = 64 columns of the column-major K×K matrix:
+//     lu_panel_kernel    one CTA factors the panel: per column a block-wide arg-max (first maximal |a|, as LAPACK's idamax),
+//                        row swap inside the panel, reciprocal scaling, rank-1 update of the panel's remaining columns
+//     lu_swap_kernel     the panel's row interchanges applied to the columns left and right of it
+//     lu_trsm_kernel     U12 = L11⁻¹·A12 (unit lower 64×64 triangle in shared memory, one matrix column per thread)
+//     lu_gemm_kernel     A22 −= L21·U12: the (2/3)·K³ flops of the factorisation, on the FP64 tensor path —
+//                        mma.sync.m8n8k4.f64 (SASS DMMA), 64×64 tiles, operands staged in shared memory with the
+//                        conflict-free pitch ≡ 4 (mod 16) doubles the coefficient-block kernel uses (sk_block.cu)
+//   then P·y, L·z = P·y and U·θ = z block by block (64-row triangle per CTA + a row-parallel update).
+//
+// An initialisation-time step, not the hot path; K ≤ 46 340 (the matrix must fit the device).
+#include <algorithm>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,46 +27,208 @@ using skh::set_error;
 
 namespace {
 
-typedef void *solver_handle;
-struct Solver {
-    void *lib = nullptr;
-    int (*create)(solver_handle *) = nullptr;
-    int (*destroy)(solver_handle) = nullptr;
-    int (*set_stream)(solver_handle, cudaStream_t) = nullptr;
-    int (*getrf_buffer)(solver_handle, int, int, double *, int, int *) = nullptr;
-    int (*getrf)(solver_handle, int, int, double *, int, double *, int *, int *) = nullptr;
-    int (*getrs)(solver_handle, int /*cublasOperation_t*/, int, int, const double *, int, const int *, double *, int, int *) = nullptr;
-    std::string error;
-};
+constexpr int NB = 64;           // panel width
+constexpr int kPitch = 68;       // shared-memory pitch of the GEMM operand tiles (≡ 4 mod 16: conflict-free fragment loads)
 
-Solver &solver() {
-    static Solver s;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        for (const char *name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"}) {
-            s.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (s.lib) break;
+// ---- panel factorisation: columns [k0, k0+nb) of rows [k0, K); one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, int *__restrict__ ipiv,
+                                                        int *__restrict__ info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    __shared__ double s_rcp;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int j = 0; j < nb; j++) {
+        const int col = k0 + j;
+        double *cj = A + (size_t)col * lda;
+        // arg-max of |a| over rows col..K-1 (first maximal element)
+        double best = -1.0;
+        int bi = col;
+        for (int r = col + tid; r < K; r += blockDim.x) {
+            const double v = fabs(cj[r]);
+            if (v > best) { best = v; bi = r; }
         }
-        if (!s.lib) { s.error = std::string("cannot load libcusolver: ") + dlerror(); return; }
-        auto sym = [&](const char *n) { void *p = dlsym(s.lib, n); if (!p && s.error.empty()) s.error = std::string("libcusolver lacks ") + n; return p; };
-        s.create = reinterpret_cast<decltype(s.create)>(sym("cusolverDnCreate"));
-        s.destroy = reinterpret_cast<decltype(s.destroy)>(sym("cusolverDnDestroy"));
-        s.set_stream = reinterpret_cast<decltype(s.set_stream)>(sym("cusolverDnSetStream"));
-        s.getrf_buffer = reinterpret_cast<decltype(s.getrf_buffer)>(sym("cusolverDnDgetrf_bufferSize"));
-        s.getrf = reinterpret_cast<decltype(s.getrf)>(sym("cusolverDnDgetrf"));
-        s.getrs = reinterpret_cast<decltype(s.getrs)>(sym("cusolverDnDgetrs"));
-    });
-    return s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            best = lane < (int)(blockDim.x >> 5) ? s_val[lane] : -1.0;
+            bi = lane < (int)(blockDim.x >> 5) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                s_piv = bi;
+                ipiv[col] = bi;
+                if (best == 0.0 && *info == 0) *info = col + 1;      // exactly singular (LAPACK's info > 0)
+                s_rcp = best == 0.0 ? 0.0 : 1.0 / cj[bi];
+            }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        // swap rows col <-> piv inside the panel
+        if (piv != col && tid < nb) {
+            double *c = A + (size_t)(k0 + tid) * lda;
+            const double t = c[col]; c[col] = c[piv]; c[piv] = t;
+        }
+        __syncthreads();
+        // scale the column below the diagonal, then rank-1 update of the panel's remaining columns
+        const double rcp = s_rcp;
+        for (int r = col + 1 + tid; r < K; r += blockDim.x) cj[r] *= rcp;
+        __syncthreads();
+        const int rem = nb - j - 1, rows = K - col - 1;
+        for (int64_t e = tid; e < (int64_t)rem * rows; e += blockDim.x) {
+            const int c = (int)(e / rows), r = (int)(e - (int64_t)c * rows) + col + 1;
+            double *cc = A + (size_t)(col + 1 + c) * lda;
+            cc[r] -= cj[r] * cc[col];
+        }
+        __syncthreads();
+    }
 }
 
-// [rows][cols] row-major  <->  column-major with leading dimension rows
-__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int64_t rows, int cols, int to_colmajor) {
-    const int64_t total = rows * cols;
+// ---- row interchanges of the panel applied to every other column (one thread per column, swaps in order)
+__global__ void lu_swap_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, const int *__restrict__ ipiv) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K - nb) return;
+    if (c >= k0) c += nb;                           // skip the panel's own columns
+    double *col = A + (size_t)c * lda;
+    for (int j = 0; j < nb; j++) {
+        const int p = ipiv[k0 + j];
+        if (p != k0 + j) { const double t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
+    }
+}
+
+// ---- U12 = L11^{-1} A12: the nb×nb unit lower triangle in shared memory, one column of A12 per thread
+__global__ void __launch_bounds__(128) lu_trsm_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb) {
+    __shared__ double L[NB][NB + 1];
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        const int r = e % nb, c = e / nb;
+        L[r][c] = A[(size_t)(k0 + c) * lda + k0 + r];
+    }
+    __syncthreads();
+    const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    double *col = A + (size_t)c * lda + k0;
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) x[i] = i < nb ? col[i] : 0.0;
+#pragma unroll
+    for (int i = 1; i < NB; i++) {
+        double s = x[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) s -= L[i][j] * x[j];
+        x[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) if (i < nb) col[i] = x[i];
+}
+
+// ---- A22 -= L21 · U12 on the FP64 tensor path: CTA tile 64×64, four warps of 32×32 (4×4 mma tiles), k = nb
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128) lu_gemm_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb) {
+    extern __shared__ __align__(16) double gemm_smem[];
+    double *As = gemm_smem;                  // As[k][row]: L21 tile, rows contiguous (as in memory)
+    double *Bs = gemm_smem + NB * kPitch;    // Bs[col][k]: U12 tile, k contiguous (as in memory)
+    const int r0 = k0 + nb + blockIdx.x * 64, c0 = k0 + nb + blockIdx.y * 64;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int e = tid; e < 64 * NB; e += 128) {
+        const int i = e & 63, k = e >> 6;
+        As[k * kPitch + i] = (k < nb && r0 + i < K) ? A[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
+    }
+    for (int e = tid; e < 64 * NB; e += 128) {
+        const int k = e & 63, j = e >> 6;
+        Bs[j * kPitch + k] = (k < nb && c0 + j < K) ? A[(size_t)(c0 + j) * lda + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    const int wr = (w & 1) * 32, wc = (w >> 1) * 32;      // this warp's 32×32 corner inside the tile
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll 4
+    for (int k = 0; k < NB; k += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = As[(k + fk) * kPitch + wr + 8 * i + fr];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = Bs[(wc + 8 * j + fr) * kPitch + k + fk];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = r0 + wr + 8 * i + fr;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int c = c0 + wc + 8 * j + 2 * fk + q;
+                if (r < K && c < K) A[(size_t)c * lda + r] -= acc[i][j][q];
+            }
+        }
+}
+
+// ---- right-hand sides, row-major Y[K][nrhs]
+__global__ void rhs_permute_kernel(const double *__restrict__ in, double *__restrict__ out, int K, int nrhs, const int *__restrict__ ipiv) {
+    // the interchanges are sequential by definition: one thread per right-hand-side column applies them in order
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nrhs) return;
+    for (int i = 0; i < K; i++) out[(size_t)i * nrhs + v] = in[(size_t)i * nrhs + v];
+    for (int i = 0; i < K; i++) {
+        const int p = ipiv[i];
+        if (p != i) { const double t = out[(size_t)i * nrhs + v]; out[(size_t)i * nrhs + v] = out[(size_t)p * nrhs + v]; out[(size_t)p * nrhs + v] = t; }
+    }
+}
+// one diagonal block: forward (unit lower) or backward (upper, non-unit) substitution; one thread per right-hand side
+__global__ void rhs_tri_kernel(const double *__restrict__ A, int64_t lda, int k0, int nb, double *__restrict__ Y, int nrhs, int upper) {
+    __shared__ double T[NB][NB + 1];
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        const int r = e % nb, c = e / nb;
+        T[r][c] = A[(size_t)(k0 + c) * lda + k0 + r];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nrhs; v += blockDim.x) {
+        double *y = Y + (size_t)k0 * nrhs + v;
+        if (!upper) {
+            for (int i = 1; i < nb; i++) {
+                double s = y[(size_t)i * nrhs];
+                for (int j = 0; j < i; j++) s -= T[i][j] * y[(size_t)j * nrhs];
+                y[(size_t)i * nrhs] = s;
+            }
+        } else {
+            for (int i = nb - 1; i >= 0; i--) {
+                double s = y[(size_t)i * nrhs];
+                for (int j = i + 1; j < nb; j++) s -= T[i][j] * y[(size_t)j * nrhs];
+                y[(size_t)i * nrhs] = s / T[i][i];
+            }
+        }
+    }
+}
+// Y[rows r_lo..r_hi) -= A[rows, k0..k0+nb) · Y[k0..k0+nb): one thread per (row, right-hand side)
+__global__ void rhs_update_kernel(const double *__restrict__ A, int64_t lda, int k0, int nb, int r_lo, int r_hi, double *__restrict__ Y, int nrhs) {
+    extern __shared__ double yb[];               // [nb][nrhs]
+    for (int e = threadIdx.x; e < nb * nrhs; e += blockDim.x) yb[e] = Y[(size_t)k0 * nrhs + e];
+    __syncthreads();
+    const int64_t total = (int64_t)(r_hi - r_lo) * nrhs;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = e / cols;
-        const int r = (int)(e % cols);
-        if (to_colmajor) out[i + (int64_t)r * rows] = in[e];
-        else out[e] = in[i + (int64_t)r * rows];
+        const int v = (int)(e / (r_hi - r_lo)), r = r_lo + (int)(e % (r_hi - r_lo));      // consecutive threads: consecutive rows
+        double s = 0.0;
+        for (int k = 0; k < nb; k++) s += A[(size_t)(k0 + k) * lda + r] * yb[k * nrhs + v];
+        Y[(size_t)r * nrhs + v] -= s;
     }
 }
 
@@ -75,14 +246,78 @@ struct DevBuf {
         if (e_ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return SK_ERR_CUDA; } \
     } while (0)
 
+namespace skk {
+
+// In-place LU with partial pivoting of the column-major K×K matrix A (leading dimension lda); ipiv[i] = row swapped with
+// row i (0-based), *info = index + 1 of the first exactly-zero pivot or 0.  ms_gemm (optional): device time of the trailing
+// updates (the DMMA part).
+cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaStream_t stream, float *ms_gemm = nullptr) {
+    constexpr size_t kGemmSmem = (size_t)2 * NB * kPitch * sizeof(double);      // 69 632 bytes
+    cudaError_t e = cudaFuncSetAttribute(lu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), stream);
+    for (int k0 = 0; k0 < K && e == cudaSuccess; k0 += NB) {
+        const int nb = std::min(NB, K - k0);
+        lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, ipiv, info);
+        if (K - nb > 0) lu_swap_kernel<<<(K - nb + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb, ipiv);
+        const int rest = K - k0 - nb;
+        if (rest > 0) {
+            lu_trsm_kernel<<<(rest + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb);
+            dim3 grid((unsigned)((rest + 63) / 64), (unsigned)((rest + 63) / 64));
+            cudaEvent_t g0 = nullptr, g1 = nullptr;
+            if (ms_gemm) { cudaEventCreate(&g0); cudaEventCreate(&g1); cudaEventRecord(g0, stream); }
+            lu_gemm_kernel<<<grid, 128, kGemmSmem, stream>>>(A, lda, K, k0, nb);
+            if (ms_gemm) {      // measurement only: serialises the factorisation
+                cudaEventRecord(g1, stream); cudaEventSynchronize(g1);
+                float t = 0; cudaEventElapsedTime(&t, g0, g1); *ms_gemm += t;
+                cudaEventDestroy(g0); cudaEventDestroy(g1);
+            }
+            count_launch(2);
+        }
+        count_launch(2);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+// solves A·X = Y for the factored A; Y (device, row-major [K][nrhs]) is overwritten by X; `work` has K·nrhs doubles
+cudaError_t lu_solve(const double *A, int64_t lda, int K, const int *ipiv, double *Y, double *work, int nrhs, cudaStream_t stream) {
+    rhs_permute_kernel<<<(nrhs + 63) / 64, 64, 0, stream>>>(Y, work, K, nrhs, ipiv);
+    count_launch();
+    const size_t sm = (size_t)NB * nrhs * sizeof(double);
+    if (sm > 48 * 1024) return cudaErrorInvalidValue;
+    for (int k0 = 0; k0 < K; k0 += NB) {               // L z = P y
+        const int nb = std::min(NB, K - k0);
+        rhs_tri_kernel<<<1, 128, 0, stream>>>(A, lda, k0, nb, work, nrhs, 0);
+        count_launch();
+        if (k0 + nb < K) {
+            const int64_t tot = (int64_t)(K - k0 - nb) * nrhs;
+            rhs_update_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 1184), 256, sm, stream>>>(A, lda, k0, nb, k0 + nb, K, work, nrhs);
+            count_launch();
+        }
+    }
+    for (int k0 = ((K - 1) / NB) * NB; k0 >= 0; k0 -= NB) {      // U x = z
+        const int nb = std::min(NB, K - k0);
+        rhs_tri_kernel<<<1, 128, 0, stream>>>(A, lda, k0, nb, work, nrhs, 1);
+        count_launch();
+        if (k0 > 0) {
+            const int64_t tot = (int64_t)k0 * nrhs;
+            rhs_update_kernel<<<(int)std::min<int64_t>((tot + 255) / 256, 1184), 256, sm, stream>>>(A, lda, k0, nb, 0, k0, work, nrhs);
+            count_launch();
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync(Y, work, (size_t)K * nrhs * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+    return e == cudaSuccess ? cudaGetLastError() : e;
+}
+
+}  // namespace skk
+
 extern "C" int sk_collocation_solve(const sk_plan *plan, const double *y, int nrhs, double *theta, uint32_t flags, void *stream_) {
     if (!plan || !y || !theta) SK_FAIL(SK_ERR_ARGUMENT, "NULL argument");
     if (nrhs < 1) SK_FAIL(SK_ERR_ARGUMENT, "nrhs < 1");
+    if (nrhs > 96) SK_FAIL(SK_ERR_UNSUPPORTED, "more than 96 right-hand sides: solve them in groups");
     if (plan->E != 1) SK_FAIL(SK_ERR_ARGUMENT, "collocation solve needs a plan without derivatives");
     const int64_t K = plan->K;
     if (K * K >= ((int64_t)1 << 31)) SK_FAIL(SK_ERR_UNSUPPORTED, "dimension(basis) above 46340: the dense factorisation is limited to 32-bit indexing");
-    Solver &S = solver();
-    if (!S.error.empty()) SK_FAIL(SK_ERR_UNSUPPORTED, S.error);
     int prev = 0;
     CKS(cudaGetDevice(&prev));
     CKS(cudaSetDevice(plan->device));
@@ -95,55 +330,61 @@ extern "C" int sk_collocation_solve(const sk_plan *plan, const double *y, int nr
     std::vector<double> grid((size_t)K * d);
     int rc = sk_grid(&plan->basis, plan->has_tr ? plan->tr : nullptr, grid.data());
     if (rc != SK_OK) return rc;
-    DevBuf dx, dA, dB, dwork, dpiv, dinfo, dy;
+    DevBuf dx, dA, dB, dwork, dpiv, dinfo;
     CKS(dx.alloc(grid.size() * sizeof(double)));
     CKS(dA.alloc((size_t)K * K * sizeof(double)));
     CKS(dB.alloc((size_t)K * nrhs * sizeof(double)));
+    CKS(dwork.alloc((size_t)K * nrhs * sizeof(double)));
     CKS(dpiv.alloc((size_t)K * sizeof(int)));
     CKS(dinfo.alloc(sizeof(int)));
     CKS(cudaMemcpyAsync(dx.p, grid.data(), grid.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     // collocation matrix, column-major K×K: A[i + k·K] = b_k(x_i)   (generic_api.jl:217-227)
     rc = sk_basis_at(plan, (const double *)dx.p, K, (double *)dA.p, K, SK_MEM_DEVICE, stream);
     if (rc != SK_OK) return rc;
-    // right-hand sides: y[K][nrhs] → column-major K×nrhs
-    const double *ysrc = y;
-    if (!(flags & SK_MEM_DEVICE)) {
-        CKS(dy.alloc((size_t)K * nrhs * sizeof(double)));
-        CKS(cudaMemcpyAsync(dy.p, y, (size_t)K * nrhs * sizeof(double), cudaMemcpyHostToDevice, stream));
-        ysrc = (const double *)dy.p;
-    }
-    const int tgrid = (int)std::min<int64_t>((K * nrhs + 255) / 256, 4096);
-    transpose_kernel<<<tgrid, 256, 0, stream>>>(ysrc, (double *)dB.p, K, nrhs, 1);
-    skk::count_launch();
-    CKS(cudaGetLastError());
-
-    solver_handle h = nullptr;
-    if (S.create(&h) != 0) SK_FAIL(SK_ERR_CUDA, "cusolverDnCreate failed");
-    struct HandleGuard { Solver &S; solver_handle h; ~HandleGuard() { S.destroy(h); } } hg{S, h};
-    if (S.set_stream(h, stream) != 0) SK_FAIL(SK_ERR_CUDA, "cusolverDnSetStream failed");
-    int lwork = 0;
-    if (S.getrf_buffer(h, (int)K, (int)K, (double *)dA.p, (int)K, &lwork) != 0) SK_FAIL(SK_ERR_CUDA, "cusolverDnDgetrf_bufferSize failed");
-    CKS(dwork.alloc((size_t)lwork * sizeof(double)));
-    if (S.getrf(h, (int)K, (int)K, (double *)dA.p, (int)K, (double *)dwork.p, (int *)dpiv.p, (int *)dinfo.p) != 0) SK_FAIL(SK_ERR_CUDA, "cusolverDnDgetrf failed");
+    // right-hand sides y[K][nrhs] (the layout of Vector{SVector{nrhs}}) stay row-major on the device
+    CKS(cudaMemcpyAsync(dB.p, y, (size_t)K * nrhs * sizeof(double), (flags & SK_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    CKS(skk::lu_factor((double *)dA.p, K, (int)K, (int *)dpiv.p, (int *)dinfo.p, stream));
     int info = 0;
     CKS(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CKS(cudaStreamSynchronize(stream));
     if (info != 0) SK_FAIL(SK_ERR_ARGUMENT, "collocation matrix is singular (LU pivot " + std::to_string(info) + " is zero)");   // Julia: SingularException
-    if (S.getrs(h, 0 /*CUBLAS_OP_N*/, (int)K, nrhs, (const double *)dA.p, (int)K, (const int *)dpiv.p, (double *)dB.p, (int)K, (int *)dinfo.p) != 0)
-        SK_FAIL(SK_ERR_CUDA, "cusolverDnDgetrs failed");
-    // θ[K][nrhs]
-    if (flags & SK_MEM_DEVICE) {
-        transpose_kernel<<<tgrid, 256, 0, stream>>>((const double *)dB.p, theta, K, nrhs, 0);
-        skk::count_launch();
-        CKS(cudaGetLastError());
-        CKS(cudaStreamSynchronize(stream));
-    } else {
-        if (!dy.p) CKS(dy.alloc((size_t)K * nrhs * sizeof(double)));
-        transpose_kernel<<<tgrid, 256, 0, stream>>>((const double *)dB.p, (double *)dy.p, K, nrhs, 0);
-        skk::count_launch();
-        CKS(cudaGetLastError());
-        CKS(cudaMemcpyAsync(theta, dy.p, (size_t)K * nrhs * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CKS(cudaStreamSynchronize(stream));
+    CKS(skk::lu_solve((const double *)dA.p, K, (int)K, (const int *)dpiv.p, (double *)dB.p, (double *)dwork.p, nrhs, stream));
+    CKS(cudaMemcpyAsync(theta, dB.p, (size_t)K * nrhs * sizeof(double), (flags & SK_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    CKS(cudaStreamSynchronize(stream));
+    return SK_OK;
+}
+
+// Measurement helper: factors a K×K matrix with the library's LU `reps` times (device pointer, overwritten) and returns the
+// mean device time; *tflops = (2/3)·K³ / time.  Used by profiles/run_solve.py.
+extern "C" int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, double *tflops, double *ms_gemm) {
+    if (!A_dev || K < 1 || K > 46340 || reps < 1 || !ms || !tflops) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
+    DevBuf copy, piv, info;
+    CKS(copy.alloc((size_t)K * K * sizeof(double)));
+    CKS(piv.alloc((size_t)K * sizeof(int)));
+    CKS(info.alloc(sizeof(int)));
+    CKS(cudaMemcpy(copy.p, A_dev, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
+    cudaEvent_t e0, e1;
+    CKS(cudaEventCreate(&e0)); CKS(cudaEventCreate(&e1));
+    float total = 0;
+    for (int r = 0; r < reps; r++) {
+        CKS(cudaMemcpy(A_dev, copy.p, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
+        CKS(cudaEventRecord(e0, nullptr));
+        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr));
+        CKS(cudaEventRecord(e1, nullptr));
+        CKS(cudaEventSynchronize(e1));
+        float t = 0;
+        CKS(cudaEventElapsedTime(&t, e0, e1));
+        total += t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms = total / reps;
+    *tflops = (2.0 / 3.0) * (double)K * K * K / (*ms * 1e-3) * 1e-12;
+    if (ms_gemm) {
+        float g = 0;
+        CKS(cudaMemcpy(A_dev, copy.p, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
+        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr, &g));
+        CKS(cudaDeviceSynchronize());
+        *ms_gemm = g;
     }
     return SK_OK;
 }

@@ -817,3 +817,49 @@ def test_randomised_parity_sweep():
     assert out.returncode == 0, out.stderr[-2000:]
     summary = json.loads(out.stdout.strip().splitlines()[-1])
     assert summary["failures"] == 0 and summary["worst_fast_scaled_error"] <= TAU, out.stdout[-2000:]
+
+
+def test_experimental_policy_functions_and_residual_sums(orc):
+    """The batched part of src/experimental.jl: make_policy_functions (:156-166: several functions over one basis from
+    one stacked coefficient vector, each followed by a bridge :242-266) and sum_of_squared_residuals (:228-233)."""
+    import torch
+    rng = np.random.default_rng(2026)
+    d, B = 3, 3
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    K = sk.dimension(basis)
+    # three policies: identity, a bridge between two bounded domains, a bridge from a bounded to a semi-infinite domain
+    pt = {"c": None, "k": sk.bridge(sk.BoundedLinear(0.5, 3.0), sk.BoundedLinear(-4.0, 4.0)),
+          "h": sk.bridge(sk.SemiInfRational(0.0, 2.0), sk.BoundedLinear(-6.0, 6.0))}
+    coef = rng.standard_normal(3 * K) * 0.3
+    x = rand_pm1(rng, (257, d))
+    pf = sk.make_policy_functions(pt, basis, coef)
+    got = np.asarray(pf(x))
+    raw = np.stack([orc.smolyak_lincomb(2, d, B, B, coef[m * K:(m + 1) * K], x)[:, 0] for m in range(3)], 1)
+    scale = np.stack([orc.smolyak_lincomb(2, d, B, B, coef[m * K:(m + 1) * K], x, absmode=True)[:, 0] for m in range(3)], 1)
+    assert np.max(np.abs(got[:, 0] - raw[:, 0]) / scale[:, 0]) <= 1e-13
+    # bridges applied to the library's own raw values are the reference's unfused operations: bit-identical to the oracle
+    raw_gpu = np.asarray(sk.stacked_linear_combination(basis, coef, x))
+    def obridge(outer, inner, v):
+        return np.array([orc.transform_from(outer, orc.transform_to(inner, float(t))[0]) for t in v])
+    assert same(got[:, 0], raw_gpu[:, 0])
+    assert same(got[:, 1], obridge(orc.BoundedLinear(0.5, 3.0), orc.BoundedLinear(-4.0, 4.0), raw_gpu[:, 1]))
+    assert same(got[:, 2], obridge(orc.SemiInfRational(0.0, 2.0), orc.BoundedLinear(-6.0, 6.0), raw_gpu[:, 2]))
+    assert set(pf.named(x)) == {"c", "k", "h"}
+    # device-resident inputs give the same numbers
+    got_dev = pf(torch.as_tensor(x).cuda()).cpu().numpy()
+    assert same(got_dev, got)
+    # length check of the reference (@argcheck lastindex(coefficients) == last(last(ranges)))
+    with pytest.raises(sk.ArgumentError):
+        sk.make_policy_functions(pt, basis, coef[:-1])
+    # residual sums: deterministic, equal to the float64 sum within rounding; the fused least-squares form agrees
+    target = got + rng.standard_normal(got.shape) * 1e-3
+    want = float(np.sum((got - target) ** 2))
+    s1 = sk.sum_abs2(got - target)
+    s2 = sk.sum_abs2(torch.as_tensor(got - target).cuda())
+    s3 = pf.residual_ssq(x, target)
+    assert s1 == s2 and abs(s1 - want) <= 1e-12 * want and abs(s3 - want) <= 1e-12 * want
+    # sum_of_squared_residuals with a user residual function vectorised over the grid
+    g = sk.grid(basis)
+    r = sk.sum_of_squared_residuals(lambda p, grid: {"euler": p["c"] - 0.1 * grid[:, 0], "budget": p["k"] - 1.0}, pf, g)
+    vals = np.asarray(pf(g))
+    assert abs(r - float(np.sum((vals[:, 0] - 0.1 * g[:, 0]) ** 2) + np.sum((vals[:, 1] - 1.0) ** 2))) <= 1e-12 * r
