@@ -6,8 +6,9 @@
 // pivoting followed by two triangular solves; this file does the same with its own kernels (no cuSOLVER, no cuBLAS):
 //
 //   blocked right-looking LU, panels of NB = 64 columns of the column-major K×K matrix:
-//     lu_panel_kernel    one CTA factors the panel: per column a block-wide arg-max (first maximal |a|, as LAPACK's idamax),
-//                        row swap inside the panel, reciprocal scaling, rank-1 update of the panel's remaining columns
+//     lu_panel_kernel    one CTA factors 8 columns of the panel at a time: per column a block-wide arg-max (first maximal
+//                        |a|, as LAPACK's idamax), row swap across the panel, reciprocal scaling, rank-1 update inside
+//                        the 8 columns; lu_panel_update_kernel brings the panel's other columns up to date on all SMs
 //     lu_swap_kernel     the panel's row interchanges applied to the columns left and right of it
 //     lu_trsm_kernel     U12 = L11⁻¹·A12 (unit lower 64×64 triangle in shared memory, one matrix column per thread)
 //     lu_gemm_kernel     A22 −= L21·U12: the (2/3)·K³ flops of the factorisation, on the FP64 tensor path —
@@ -31,14 +32,16 @@ constexpr int NB = 64;           // panel width
 constexpr int kPitch = 68;       // shared-memory pitch of the GEMM operand tiles (≡ 4 mod 16: conflict-free fragment loads)
 
 // ---- panel factorisation: columns [k0, k0+nb) of rows [k0, K); one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, int *__restrict__ ipiv,
-                                                        int *__restrict__ info) {
+// (sub-panel [jb, jb+ib) of the panel: pivot search, swap across the WHOLE panel, scaling, rank-1 updates inside the
+// sub-panel only; the panel's columns to the right are brought up to date by lu_panel_update_kernel on all SMs)
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, int jb, int ib,
+                                                        int *__restrict__ ipiv, int *__restrict__ info) {
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_piv;
     __shared__ double s_rcp;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int j = 0; j < nb; j++) {
+    for (int j = jb; j < jb + ib; j++) {
         const int col = k0 + j;
         double *cj = A + (size_t)col * lda;
         // arg-max of |a| over rows col..K-1 (first maximal element)
@@ -84,13 +87,45 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, 
         const double rcp = s_rcp;
         for (int r = col + 1 + tid; r < K; r += blockDim.x) cj[r] *= rcp;
         __syncthreads();
-        const int rem = nb - j - 1, rows = K - col - 1;
+        const int rem = jb + ib - j - 1, rows = K - col - 1;
         for (int64_t e = tid; e < (int64_t)rem * rows; e += blockDim.x) {
             const int c = (int)(e / rows), r = (int)(e - (int64_t)c * rows) + col + 1;
             double *cc = A + (size_t)(col + 1 + c) * lda;
             cc[r] -= cj[r] * cc[col];
         }
         __syncthreads();
+    }
+    // rows [jb, jb+ib) of the panel's columns to the right become rows of U: u = L_bb^{-1} a_b, one column per thread,
+    // in place (lu_panel_update_kernel then reads them)
+    const int right = nb - jb - ib, rb = k0 + jb;
+    if (tid < right) {
+        double *c = A + (size_t)(rb + ib + tid) * lda + rb;
+        double x[8];
+        for (int i = 0; i < ib; i++) {
+            double sacc = c[i];
+            for (int jj = 0; jj < i; jj++) sacc -= A[(size_t)(rb + jj) * lda + rb + i] * x[jj];
+            x[i] = sacc;
+        }
+        for (int i = 1; i < ib; i++) c[i] = x[i];
+    }
+}
+
+// ---- the panel's columns right of a factored sub-panel: a_r -= L_rb u with u = the ib rows of U the panel kernel
+// solved in place; grid: (row tiles of 256, columns)
+constexpr int IB = 8;
+__global__ void __launch_bounds__(256) lu_panel_update_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int jb, int ib) {
+    __shared__ double u[IB];
+    const int c = k0 + jb + ib + blockIdx.y;            // column being updated
+    const int rb = k0 + jb;                             // first row / column of the sub-panel
+    double *col = A + (size_t)c * lda;
+    if (threadIdx.x < ib) u[threadIdx.x] = col[rb + threadIdx.x];      // rows of U, solved by the panel kernel
+    __syncthreads();
+    const int r = rb + ib + blockIdx.x * 256 + threadIdx.x;
+    if (r < K) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < IB; t++) if (t < ib) s += A[(size_t)(rb + t) * lda + r] * u[t];
+        col[r] -= s;
     }
 }
 
@@ -257,7 +292,17 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
     if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), stream);
     for (int k0 = 0; k0 < K && e == cudaSuccess; k0 += NB) {
         const int nb = std::min(NB, K - k0);
-        lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, ipiv, info);
+        for (int jb = 0; jb < nb; jb += IB) {
+            const int ib = std::min(IB, nb - jb);
+            lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, jb, ib, ipiv, info);
+            const int right = nb - jb - ib, below = K - (k0 + jb + ib);
+            if (right > 0) {
+                dim3 ug((unsigned)std::max(1, (below + 255) / 256), (unsigned)right);
+                lu_panel_update_kernel<<<ug, 256, 0, stream>>>(A, lda, K, k0, jb, ib);
+                count_launch();
+            }
+            count_launch();
+        }
         if (K - nb > 0) lu_swap_kernel<<<(K - nb + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb, ipiv);
         const int rest = K - k0 - nb;
         if (rest > 0) {
@@ -273,7 +318,7 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
             }
             count_launch(2);
         }
-        count_launch(2);
+        count_launch(1);      // the swap kernel
         e = cudaGetLastError();
     }
     return e;
