@@ -12,8 +12,11 @@
 #     basis = smolyak_basis(Chebyshev, InteriorGrid2(), SmolyakParameters(4), 6) ∘ ct
 #     θ  = randn(dimension(basis))
 #     xs = [ntuple(_ -> rand(), 6) for _ in 1:10^6]          # Vector{NTuple{6,Float64}}
-#     ys = linear_combination(basis, θ, ∂gradient(6), xs)     # Vector{SVector{7,Float64}}, on the GPU
-#     C  = collocation_matrix_gpu(basis, xs)                  # Matrix{Float64}, on the GPU
+#     D  = ∂gradient(6)
+#     ys = linear_combination.(basis, Ref(θ), D.(xs))         # the reference's own idiom (test/test_generic_api.jl:22):
+#                                                             # the broadcast is intercepted and runs as ONE GPU batch
+#     ys = linear_combination(basis, θ, D, xs)                # the same, explicit batched method
+#     C  = collocation_matrix(basis, xs)                      # Matrix{Float64} (generic_api.jl:217), on the GPU
 #
 # Memory: Julia's `Vector{NTuple{d,Float64}}`, `Vector{SVector{M,Float64}}`, `d×n Matrix{Float64}`
 # and `Matrix{Float64}` already have the layouts the C ABI takes, so pointers are passed through
@@ -26,7 +29,7 @@ using SpectralKit: Chebyshev, SmolyakBasis, SmolyakIndices, TransformedBasis, Bo
     𝑑Derivatives, ∂Derivatives, Partials, _partials_canonical_expansion
 using StaticArrays
 
-export ∂gradient, collocation_matrix_gpu, basis_at_gpu, SKPlan
+export ∂gradient, collocation_matrix_gpu, basis_at_gpu, collocation_solve_gpu, SKPlan
 
 const libsk = get(ENV, "SPECTRALKIT_B200_LIB", joinpath(@__DIR__, "..", "lib", "libspectralkit_b200.so"))
 
@@ -105,8 +108,13 @@ mutable struct SKPlan
     end
 end
 
+# plan cache; the header promises re-entrancy, so the Dict is only touched under a lock (plans themselves are immutable
+# and may be used from several tasks at once)
 const PLANS = Dict{Any,SKPlan}()
-plan_for(basis; kw...) = get!(() -> SKPlan(basis; kw...), PLANS, (basis, kw))
+const PLANS_LOCK = ReentrantLock()
+plan_for(basis; kw...) = lock(PLANS_LOCK) do
+    get!(() -> SKPlan(basis; kw...), PLANS, (basis, kw))
+end
 
 # ---- batched linear_combination (generic_api.jl:114-138) ----------------------------------------
 # univariate: xs::AbstractVector{Float64}; `𝑑^D` requests derivatives (derivatives.jl:66-107)
@@ -145,6 +153,48 @@ function SpectralKit.linear_combination(basis, θ::Vector{SVector{M,Float64}}, x
     out
 end
 
+# ---- the reference's calling convention for derivatives, batched ----------------------------------
+# `(𝑑^D)(x)` (derivatives.jl:105-107) seeds one point; `(𝑑^D).(xs)` is a Vector{𝑑Expansion{D+1,Float64}} whose first
+# coefficients are the points (the seeds (1, 0, …) are implied and re-created on the device).
+function SpectralKit.linear_combination(basis, θ::Vector{Float64}, xs::Vector{SpectralKit.𝑑Expansion{Dp1,Float64}};
+                                        exact::Bool = false) where {Dp1}
+    SpectralKit.linear_combination(basis, θ, Float64[x.coefficients[1] for x in xs]; D = 𝑑Derivatives{Dp1 - 1}(), exact)
+end
+# `D(x)` with D::∂Derivatives (derivatives.jl:455) wraps one point; `D.(xs)` is a Vector{∂CoordinateExpansion}: the request
+# travels in the element type, the points are the first coefficients of the wrapped coordinates.
+function SpectralKit.linear_combination(basis, θ::Vector{Float64},
+                                        xs::Vector{<:SpectralKit.∂CoordinateExpansion{D,<:NTuple{N,Any}}}; exact::Bool = false) where {D,N}
+    isempty(xs) && return SpectralKit.∂Expansion[]
+    pts = NTuple{N,Float64}[map(c -> c.coefficients[1], x.x) for x in xs]
+    SpectralKit.linear_combination(basis, θ, first(xs).∂D, pts; exact)
+end
+
+# ---- broadcast hooks (SURVEY.md §8(b)): the reference API is pointwise and callers batch by broadcasting
+# (`linear_combination.(basis, Ref(φ), y)`, test/test_generic_api.jl:22; `basis_at.(…)`, `l.(xs)` for a LinearCombination).
+# These methods turn exactly those broadcasts over Vector arguments into one library call; anything else falls through
+# to Base's broadcast and the reference's pointwise methods.
+const _Points = Union{Vector{Float64},Vector{<:NTuple{N,Float64} where N},Vector{<:SVector{N,Float64} where N},
+                      Vector{<:SpectralKit.𝑑Expansion},Vector{<:SpectralKit.∂CoordinateExpansion}}
+_unref(x::Base.RefValue) = x[]
+_unref(x) = x
+function Base.Broadcast.broadcasted(::typeof(SpectralKit.linear_combination), basis::SpectralKit.FunctionBasis,
+                                    θ::Union{Base.RefValue{Vector{Float64}},Tuple{Vector{Float64}}}, xs::_Points)
+    θv = θ isa Tuple ? θ[1] : _unref(θ)
+    xs isa Vector{<:Union{NTuple,SVector}} ? SpectralKit.linear_combination(basis, θv, nothing, xs) :
+                                             SpectralKit.linear_combination(basis, θv, xs)
+end
+function Base.Broadcast.broadcasted(l::SpectralKit.LinearCombination{<:SpectralKit.FunctionBasis,Vector{Float64}}, xs::_Points)
+    xs isa Vector{<:Union{NTuple,SVector}} ? SpectralKit.linear_combination(l.basis, l.θ, nothing, xs) :
+                                             SpectralKit.linear_combination(l.basis, l.θ, xs)
+end
+# `collect.(basis_at.(basis, xs))` materialises the same numbers as a collocation matrix; the lazy per-point iterators of
+# the reference have no batched counterpart, so the hook returns the rows of the matrix
+function Base.Broadcast.broadcasted(::typeof(SpectralKit.basis_at), basis::SpectralKit.FunctionBasis,
+                                    xs::Union{Vector{Float64},Vector{<:NTuple{N,Float64} where N},Vector{<:SVector{N,Float64} where N}})
+    C = collocation_matrix_gpu(basis, xs)
+    [view(C, i, :) for i in axes(C, 1)]
+end
+
 # ---- collocation_matrix / basis_at (generic_api.jl:217-227): column-major n×K, as the reference ----
 function collocation_matrix_gpu(basis, xs::Vector{Float64} = collect(grid(basis)))
     p = plan_for(basis)
@@ -163,6 +213,17 @@ function collocation_matrix_gpu(basis, xs::Vector{<:Union{NTuple{N,Float64},SVec
     C
 end
 const basis_at_gpu = collocation_matrix_gpu
+
+# the reference's own name (generic_api.jl:217): `collocation_matrix(basis, x)` for a Vector of points goes to the GPU,
+# `collocation_matrix(basis)` evaluates at the basis' own grid.  (Deliberate method overriding for these argument types:
+# this is what "drop-in" means; every other iterable of points keeps the reference's CPU method.)
+SpectralKit.collocation_matrix(basis::SpectralKit.FunctionBasis, xs::Vector{Float64}) = collocation_matrix_gpu(basis, xs)
+SpectralKit.collocation_matrix(basis::SpectralKit.FunctionBasis, xs::Vector{<:Union{NTuple{N,Float64},SVector{N,Float64}}}) where {N} =
+    collocation_matrix_gpu(basis, xs)
+function SpectralKit.collocation_matrix(basis::SpectralKit.FunctionBasis)
+    g = collect(grid(basis))
+    collocation_matrix_gpu(basis, g isa Vector{Float64} ? g : NTuple{length(first(g)),Float64}[Tuple(p) for p in g])
+end
 
 # ---- fitting: θ = collocation_matrix(basis) \ y on the basis' own grid (docs/src/index.md:92) ----
 "`collocation_matrix(basis) \\ y` with the matrix generated and factorised on the GPU; `y` are the values at `grid(basis)`."
