@@ -123,6 +123,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def bind_to_gpu_numa_node(local: int):
+    """Pins this rank to the CPUs of its GPU's NUMA node before any pinned buffer is allocated (first touch then places the
+    staging memory next to the GPU's PCIe root).  Best effort: returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {local} ({bus}): no NUMA information"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {local}: node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {local} ({bus}) -> NUMA node {node}, {len(cpus)} CPUs"
+    except Exception as e:       # no sysfs, no permission, old torch: run unpinned
+        return f"unpinned ({type(e).__name__})"
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -138,6 +161,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa else "disabled"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner / debug lines stay off stdout (one JSON line there)
@@ -319,7 +343,7 @@ def run_ours(args):
                          "hbm_gbs": hbm_gbs,
                          "hbm_frac_of_measured": hbm_gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None},
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": e2e_n * D * 8 + K * 8, "d2h_bytes_per_step": e2e_n * (D + 1) * 8,
-                    "points_per_gpu": e2e_n, "ms_per_step": e2e_ms},
+                    "points_per_gpu": e2e_n, "ms_per_step": e2e_ms, "host_affinity_rank0": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -345,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=100_000_000, help="points per GPU per step")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --points per GPU; strong: --points in total, ceil(P/N) per rank")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin ranks to the NUMA node of their GPU")
     ap.add_argument("--gather", action="store_true", help="also time C2: an in-place NCCL all-gather of the result slices (N > 1)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,7 +1,7 @@
 """Randomised parity sweep: many (grid family, d, B, M, request, transformations, nvec) configurations at small sizes,
 CUDA library vs CPU oracle — exact mode bit for bit, fast mode within TAU·S.  Complements tests/ (fixed cases) by
 walking the dispatch table: full-size and 128-thread leaf variants of every depth, the generic nested kernel (M < B),
-the general-∂ kernel, the block kernel and the per-vector path.
+the general-∂ kernel, the block kernel and the per-vector path; and basis_at (chunked tables, TMA stores) bit for bit.
 usage: python profiles/fuzz_parity.py [n_configs] [seed] > profiles/r1_fuzz_parity.jsonl"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -77,12 +77,21 @@ for it in range(N):
         paths[("exact-unsupported", fp)] = paths.get(("exact-unsupported", fp), 0) + 1
     fa = np.asarray(sk.linear_combination(basis, theta, pts)).reshape(want.shape)
     ok_exact = same(ex, want)
+    # basis_at / collocation_matrix (round 2: chunked-table kernel with TMA stores): bit for bit against the oracle
+    ok_basis = True
+    if kind != "block":
+        m = min(n, 24)
+        bw = orc.smolyak_basis_at(code, d, B, M, y[:m], trs=trs_or, spec=ospec)                 # (K, m, E)
+        bg = np.asarray(sk.basis_at(basis, spec(y[:m]) if spec is not None else y[:m]))
+        bg = bg[:, :, None] if bg.ndim == 2 else bg
+        ok_basis = same(bg, bw.transpose(1, 0, 2))
+        paths[("basis_at", int(bw.shape[2]))] = paths.get(("basis_at", int(bw.shape[2])), 0) + 1
     with np.errstate(all="ignore"):
         err = float(np.nanmax(np.where(scale > 0, np.abs(fa - want) / scale, np.where(fa == want, 0.0, np.inf)))) if fa.size else 0.0
     worst = max(worst, err)
-    if not ok_exact or not err <= TAU:
+    if not ok_exact or not ok_basis or not err <= TAU:
         bad += 1
         print(json.dumps({"FAIL": True, "code": code, "d": d, "B": B, "M": M, "kind": kind, "nvec": nvec, "tr": use_tr, "n": n, "fast_path": fp,
-                          "exact_bitwise": ok_exact, "fast_scaled_err": err}), flush=True)
+                          "exact_bitwise": ok_exact, "basis_at_bitwise": ok_basis, "fast_scaled_err": err}), flush=True)
 print(json.dumps({"configs": N, "seed": seed, "failures": bad, "worst_fast_scaled_error": worst, "tolerance": TAU,
                   "paths (kind, fast_path)": {f"{k[0]}:{k[1]}": v for k, v in sorted(paths.items())}, "seconds": time.time() - t0}))

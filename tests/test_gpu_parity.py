@@ -863,3 +863,29 @@ def test_experimental_policy_functions_and_residual_sums(orc):
     r = sk.sum_of_squared_residuals(lambda p, grid: {"euler": p["c"] - 0.1 * grid[:, 0], "budget": p["k"] - 1.0}, pf, g)
     vals = np.asarray(pf(g))
     assert abs(r - float(np.sum((vals[:, 0] - 0.1 * g[:, 0]) ** 2) + np.sum((vals[:, 1] - 1.0) ** 2))) <= 1e-12 * r
+
+
+def test_uni_constant_bank_slots_shared_between_derivative_orders(orc):
+    """the constant-bank θ slots of the univariate fast kernels are one set per device for every derivative
+    order.  Two streams evaluate order 0 and order 1 with different θ concurrently, many times: each result must be the
+    one its own θ gives (a private slot counter per template instantiation let one stream overwrite the other's θ)."""
+    import torch
+    n, N = 1 << 18, 64                                                   # n >= 2^17: the constant-bank path
+    b = sk.Chebyshev(sk.InteriorGrid(), N) @ sk.BoundedLinear(-2, 3)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    y = torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * 5 - 2
+    th0 = torch.randn(N, generator=gen, device="cuda", dtype=torch.float64)
+    th1 = torch.randn(N, generator=gen, device="cuda", dtype=torch.float64) * 3 + 1
+    want0 = sk.linear_combination(b, th0, y).clone()
+    want1 = sk.linear_combination(b, th1, sk.d(y)).clone()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs0, outs1 = [], []
+    for _ in range(12):
+        with torch.cuda.stream(s0):
+            outs0.append(sk.linear_combination(b, th0, y))
+        with torch.cuda.stream(s1):
+            outs1.append(sk.linear_combination(b, th1, sk.d(y)))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, want0) for o in outs0)
+    assert all(torch.equal(o, want1) for o in outs1)

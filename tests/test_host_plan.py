@@ -258,3 +258,57 @@ def test_augment_coefficients_golden():
     b1 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(2, 1), 3)
     b2 = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4, 3), 3)
     assert (sk.augment_coefficients(b1, b2, g["ag_theta1"]) == g["ag_theta2"]).all()
+
+
+def test_oversized_bases_are_refused_with_a_status_code():
+    """nothing may unwind through the C ABI; index sets beyond SK_MAX_TERMS are refused up front
+    (d = 16, B = M = 8, InteriorGrid would be 4.3e8 terms: 13.7 GB of index table)."""
+    import ctypes as C
+    L = sk._lib
+    desc = L.BasisDesc(L.SK_BASIS_SMOLYAK, L.SK_GRID_INTERIOR, 0, 16, 8, 8)
+    K = C.c_int64(0)
+    assert L.lib.sk_dimension(C.byref(desc), C.byref(K)) in (L.SK_OK, L.SK_ERR_UNSUPPORTED)
+    h = C.c_void_p()
+    ds = L.DerivSpec(0, 0, None, 0)
+    rc = L.lib.sk_plan_create(C.byref(desc), None, C.byref(ds), 0, C.byref(h))
+    assert rc == L.SK_ERR_UNSUPPORTED and b"SK_MAX_TERMS" in L.lib.sk_last_error()
+    out = (C.c_int32 * 16)()
+    assert L.lib.sk_smolyak_indices(C.byref(desc), out) == L.SK_ERR_UNSUPPORTED
+
+
+def test_multi_gpu_and_experimental_entries_fail_cleanly_without_a_device():
+    """The new entry points validate their arguments and report SK_ERR_NO_DEVICE / SK_ERR_ARGUMENT on a box without
+    GPUs (no CPU fallback, no crash)."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    L = sk._lib
+    devs = (C.c_int * 2)(0, 1)
+    h = C.c_void_p()
+    assert L.lib.sk_comm_create(2, devs, C.byref(h)) == L.SK_ERR_NO_DEVICE
+    assert L.lib.sk_comm_create(0, devs, C.byref(h)) == L.SK_ERR_ARGUMENT
+    assert L.lib.sk_comm_destroy(None) == L.SK_OK
+    r = (C.c_double * 4)(1, 2, 3, 4)
+    res = C.c_double(-1)
+    assert L.lib.sk_sum_abs2(r, 4, C.byref(res), L.SK_MEM_HOST, 0, None) == L.SK_ERR_NO_DEVICE
+    assert L.lib.sk_sum_abs2(r, 0, C.byref(res), L.SK_MEM_HOST, 0, None) == L.SK_OK and res.value == 0.0
+    assert L.lib.sk_policy_functions(None, r, 4, 1, None, r, 1, r, L.SK_MEM_HOST, None) == L.SK_ERR_ARGUMENT
+    with pytest.raises(sk.CudaError):
+        sk.Comm([0])
+
+
+def test_bridge_and_policy_function_host_side_checks():
+    """Argument checking of the Experimental mirror happens before any device work (src/experimental.jl:160-162)."""
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(2), 2)
+    K = sk.dimension(basis)
+    pt = {"a": None, "b": sk.bridge(sk.BoundedLinear(0, 1), sk.BoundedLinear(-1, 1))}
+    with pytest.raises(sk.ArgumentError):
+        sk.make_policy_functions(pt, basis, np.zeros(2 * K - 1))
+    with pytest.raises(sk.ArgumentError):
+        sk.bridge(sk.BoundedLinear(0, 1), "not a transformation")
+    pf = sk.make_policy_functions(pt, basis, np.zeros(2 * K))
+    assert pf.names == ["a", "b"] and pf.M == 2 and pf.K == K
+    b = sk.bridge(sk.BoundedLinear(0, 1), sk.SemiInfRational(0, 2)).inverse()
+    assert isinstance(b.outer, sk.SemiInfRational) and isinstance(b.inner, sk.BoundedLinear)
+    assert sk.experimental.policy_coefficients_dimension(pt, basis) == 2 * K
