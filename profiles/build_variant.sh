@@ -25,6 +25,6 @@ EOS
 nvcc $NVF -c $ROOT/exp/obj/stubs.cu -o $ROOT/exp/obj/stubs.o
 fi
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $ROOT/exp/lib_$NAME.so \
-  $S/sk_host.o $S/sk_kernels.o $S/sk_nested.o $S/sk_general.o $S/sk_block.o $S/sk_solve.o $S/sk_leaf.o $S/sk_api.o \
+  $S/sk_host.o $S/sk_kernels.o $S/sk_nested.o $S/sk_general.o $S/sk_block.o $S/sk_basis.o $S/sk_solve.o $S/sk_experimental.o $S/sk_multi.o $S/sk_leaf.o $S/sk_api.o \
   $ROOT/exp/obj/g2g_$NAME.o $ROOT/exp/obj/stubs.o -lquadmath -ldl
 ls -la $ROOT/exp/lib_$NAME.so

@@ -131,6 +131,7 @@ struct BasisParams {
     double *out;
     int64_t n, ld, K;
     int d, E, ncomp, facw, tw, n_chunks, max_rows, use_tma, pb, nf;  // pb: points per TMA box (pb·E <= 256); nf: factors per term (values)
+    int substride;                                                   // doubles between the sub-boxes of a staging tile (128-byte multiples: TMA source alignment)
     const ChunkHdr *hdr;
     const uint16_t *build, *fac;
     sk_transform tr[SK_MAX_DIM];
@@ -265,11 +266,11 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
     const size_t xj_bytes = ((size_t)d * JW * kP * 8 + 127) & ~(size_t)127;
     double *rows = reinterpret_cast<double *>(smem_raw + xj_bytes);                     // [row][JW][32]
     const size_t rows_bytes = ((size_t)q.max_rows * JW * kP * 8 + 127) & ~(size_t)127;
-    const size_t tile_bytes = ((size_t)TW * kP * E * 8 + 127) & ~(size_t)127;
+    const size_t tile_bytes = ((size_t)(kP / q.pb) * q.substride * 8 + 127) & ~(size_t)127;
     double *stage = reinterpret_cast<double *>(smem_raw + xj_bytes + rows_bytes + (size_t)w * 2 * tile_bytes);
     const int nsub = kP / q.pb;                                                         // TMA boxes per tile along the points
     // this lane's slot in term 0 of a staging tile ([sub-box][term][point in box][component]) and the stride between terms
-    const uint32_t lane_off = (uint32_t)(((lane / q.pb) * TW) * (q.pb * E) + (lane % q.pb) * E) * 8u, tstride = (uint32_t)(q.pb * E) * 8u;
+    const uint32_t lane_off = (uint32_t)((lane / q.pb) * q.substride + (lane % q.pb) * E) * 8u, tstride = (uint32_t)(q.pb * E) * 8u;
     int buf = 0;
 
     for (int64_t p0 = (int64_t)blockIdx.x * kP; p0 < q.n; p0 += (int64_t)gridDim.x * kP) {
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
                     __syncwarp();
                     if (lane == 0) {
                         for (int sb = 0; sb < nsub; sb++)
-                            tma_store_2d(&tmap, st + (size_t)sb * TW * q.pb * E, (int)((p0 + (int64_t)sb * q.pb) * E), (int)k0);
+                            tma_store_2d(&tmap, st + (size_t)sb * q.substride, (int)((p0 + (int64_t)sb * q.pb) * E), (int)k0);
                         tma_commit();
                         tma_wait_read_1();                          // the other buffer's read has completed
                     }
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
                         for (int e = lane; e < row_elems; e += 32) {
                             const int pt = e / E, cc = e - pt * E;
                             if (p0 + pt < q.n)
-                                __stcs(g + e, st[((size_t)(pt / q.pb) * TW + t) * (q.pb * E) + (size_t)(pt % q.pb) * E + cc]);
+                                __stcs(g + e, st[(size_t)(pt / q.pb) * q.substride + (size_t)t * (q.pb * E) + (size_t)(pt % q.pb) * E + cc]);
                         }
                     }
                     __syncwarp();
@@ -416,7 +417,12 @@ cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t 
     // staging tile of one warp: TW terms × 32 points × E doubles, 2-4 KB (one 16 KB buffer pair per warp at E = 64)
     int tw = 8;                                                     // TW terms per warp tile: a power of two, 2-4 KB per tile
     while (tw > 1 && tw * E > 16) tw >>= 1;
-    const size_t tile_bytes = (((size_t)tw * kP * E * 8) + 127) & ~(size_t)127;
+    // TMA box: pb points × E components per row (<= 256 elements), TW rows; the sub-boxes of a staging tile start on
+    // 128-byte boundaries (source alignment of cp.async.bulk.tensor)
+    int pb = kP;
+    while (pb * E > 256) pb >>= 1;
+    const int substride = (tw * pb * E + 15) & ~15;
+    const size_t tile_bytes = (((size_t)(kP / pb) * substride * 8) + 127) & ~(size_t)127;
     const size_t xj_bytes = ((size_t)d * JW * kP * 8 + 127) & ~(size_t)127;
     const size_t stage_bytes = (size_t)kWarps * 2 * tile_bytes;
     const size_t budget = 200 * 1024;
@@ -460,10 +466,7 @@ cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t 
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
     }
     for (int c = 0; c < plan.ncomp; c++) for (int j = 0; j < d; j++) q.orders[c][j] = (int8_t)plan.orders[c][j];
-    // TMA box: pb points × E components per row (<= 256 elements), TW rows
-    int pb = kP;
-    while (pb * E > 256) pb >>= 1;
-    q.pb = pb;
+    q.pb = pb; q.substride = substride;
     static const int no_tma = [] { const char *e = getenv("SK_BASIS_NO_TMA"); return e ? atoi(e) : 0; }();
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof tmap);
