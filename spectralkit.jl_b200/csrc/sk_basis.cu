@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <mutex>
 #include <vector>
 
@@ -389,7 +390,7 @@ EncodeTiledFn encode_tiled() {
 struct ProgramCache {
     std::mutex mu;
     struct Entry { const sk_plan *plan; int jw, device; BasisProgram host; ChunkHdr *d_hdr; uint16_t *d_build, *d_fac; int tw, row_cap; };
-    std::vector<Entry> entries;
+    std::list<Entry> entries;      // a list: entries keep their address while other threads add theirs
 };
 ProgramCache &cache() { static ProgramCache c; return c; }
 
@@ -399,11 +400,11 @@ ProgramCache &cache() { static ProgramCache c; return c; }
 void smolyak_tile_basis_forget(const sk_plan *plan) {
     ProgramCache &pc = cache();
     std::lock_guard<std::mutex> lk(pc.mu);
-    for (size_t i = 0; i < pc.entries.size();) {
-        if (pc.entries[i].plan == plan) {
-            cudaFree(pc.entries[i].d_hdr); cudaFree(pc.entries[i].d_build); cudaFree(pc.entries[i].d_fac);
-            pc.entries.erase(pc.entries.begin() + (long)i);
-        } else i++;
+    for (auto it = pc.entries.begin(); it != pc.entries.end();) {
+        if (it->plan == plan) {
+            cudaFree(it->d_hdr); cudaFree(it->d_build); cudaFree(it->d_fac);
+            it = pc.entries.erase(it);
+        } else ++it;
     }
 }
 
