@@ -112,12 +112,10 @@ typedef struct sk_plan_info {
 #define SK_MEM_DEVICE 1u        /* x, theta, out are device pointers on the plan's device */
 #define SK_MODE_FAST 0u         /* FMA-contracted, nested evaluation; within the stated tolerance */
 #define SK_MODE_EXACT 2u        /* reference operation order, no contraction: bit-identical to the
-                                   reference restatement (sequential sum, mul-then-add).  For
-                                   sk_linear_combination this mode keeps every dimension's full table
-                                   on chip: Smolyak bases with d * l(B) * (max order + 1) > 896 return
-                                   SK_ERR_UNSUPPORTED there (SK_MODE_FAST serves them).  sk_basis_at /
-                                   collocation matrices are always bit-identical and have no such
-                                   limit (tables are streamed chunk by chunk, csrc/sk_basis.cu) */
+                                   reference restatement (sequential sum, mul-then-add), for bases of
+                                   any size (full tables on chip where they fit, tables streamed chunk by
+                                   chunk otherwise).  sk_basis_at / collocation matrices are always
+                                   bit-identical */
 
 /* ---------------------------------------------------------------- library */
 const char *sk_version(void);

@@ -542,8 +542,13 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         CK(skk::smolyak_block_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
-    if (!skk::smolyak_direct_fits(*plan, false))
-        SK_FAIL(SK_ERR_UNSUPPORTED, "basis too large for the bit-identical direct kernel: d * l(B) * (order + 1) doubles per point for 32 points exceed shared memory" "(fast mode serves such bases)");
+    if (!skk::smolyak_direct_fits(*plan, false)) {
+        // full tables of 32 points exceed shared memory: the chunked-table kernel keeps the reference's order too
+        if (!skk::smolyak_tile_lincomb_supported(*plan, nvec))
+            SK_FAIL(SK_ERR_UNSUPPORTED, "bit-identical evaluation of this request needs more than 64 components or 512 coefficient vectors on a basis whose tables exceed shared memory (fast mode serves it)");
+        CK(skk::smolyak_tile_lincomb_exact(*plan, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
     CK(skk::smolyak_direct_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
     return SK_OK;
 }

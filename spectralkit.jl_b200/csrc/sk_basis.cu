@@ -133,6 +133,8 @@ struct BasisParams {
     int64_t n, ld, K;
     int d, E, ncomp, facw, tw, n_chunks, max_rows, use_tma, pb, nf;  // pb: points per TMA box (pb·E <= 256); nf: factors per term (values)
     int substride;                                                   // doubles between the sub-boxes of a staging tile (128-byte multiples: TMA source alignment)
+    const double *theta;                                             // exact linear_combination: θ[K][nvec]
+    int nvec;
     const ChunkHdr *hdr;
     const uint16_t *build, *fac;
     sk_transform tr[SK_MAX_DIM];
@@ -373,6 +375,126 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
     if (q.use_tma && lane == 0) tma_wait_all();
 }
 
+// ---- bit-identical linear_combination on the same chunked tables (SK_MODE_EXACT for bases of any size):
+// the reference's sequential s = s + θ_k·b_k (generic_api.jl:114-128: multiply, then add, never fused) in term order.
+// One thread owns the sums of one point (lane) for the items of its warp — components of a ∂ request (item = component,
+// warp w takes items w, w+8, …) or groups of 8 coefficient vectors (SVector coefficients, values only) — and walks ALL
+// terms of every chunk in order; only the table rows are shared.  A checker-speed path (the products are re-formed per
+// item), like the direct kernel it replaces for large bases.
+constexpr int kMaxItems = 8;      // items per warp: 64 components, or 64 groups of 8 = 512 coefficient vectors
+template <int JW, bool BIG>
+__global__ void __launch_bounds__(kP * kWarps) smolyak_tile_lincomb_kernel(const __grid_constant__ BasisParams q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int d = q.d;
+    double *xj = reinterpret_cast<double *>(smem_raw);
+    const size_t xj_bytes = ((size_t)d * JW * kP * 8 + 127) & ~(size_t)127;
+    double *rows = reinterpret_cast<double *>(smem_raw + xj_bytes);
+    const bool vecs = q.nvec > 1;
+    const int n_items = vecs ? (q.nvec + 7) / 8 : q.E;
+    constexpr int NW = BIG ? 8 : 4;
+    for (int64_t p0 = (int64_t)blockIdx.x * kP; p0 < q.n; p0 += (int64_t)gridDim.x * kP) {
+        const int64_t p = min(p0 + lane, q.n - 1);
+        __syncthreads();
+        for (int j = w; j < d; j += kWarps) {
+            double v[JW];
+            skd::to_pm1_jet<JW>(q.tr[j], q.x[p * d + j], v);
+#pragma unroll
+            for (int r = 0; r < JW; r++) xj[((size_t)j * JW + r) * kP + lane] = v[r];
+        }
+        if (w == kWarps - 1) {
+#pragma unroll
+            for (int r = 0; r < JW; r++) rows[(size_t)r * kP + lane] = r == 0 ? 1.0 : 0.0;
+        }
+        double s[kMaxItems][8];                              // [item of this warp][vector of the group] (components: [.][0])
+#pragma unroll
+        for (int i = 0; i < kMaxItems; i++)
+#pragma unroll
+            for (int v = 0; v < 8; v++) s[i][v] = 0.0;
+        for (int c = 0; c < q.n_chunks; c++) {
+            const ChunkHdr h = q.hdr[c];
+            __syncthreads();
+            {
+                const uint16_t *bl = q.build + h.build_off;
+                for (int j = 0; j < d; j++) {
+                    const int maxidx = bl[0], cnt = bl[1];
+                    if (cnt > 0 && (j % kWarps) == w) {
+                        Jet<JW> X, fp = skd::jet_one<JW>(), fpp, f;
+#pragma unroll
+                        for (int r = 0; r < JW; r++) { X.c[r] = xj[((size_t)j * JW + r) * kP + lane]; fpp.c[r] = X.c[r]; }
+                        int nx = 0, want = bl[2];
+                        for (int i = 2; i <= maxidx; i++) {
+                            f = skd::cheb_step_exact<JW>(X, fp, fpp); fpp = fp; fp = f;
+                            if (i == want) {
+                                double *r0 = rows + (size_t)bl[3 + 2 * nx] * JW * kP + lane;
+#pragma unroll
+                                for (int r = 0; r < JW; r++) r0[(size_t)r * kP] = f.c[r];
+                                nx++;
+                                want = nx < cnt ? bl[2 + 2 * nx] : 0;
+                            }
+                        }
+                    }
+                    bl += 2 + 2 * cnt;
+                }
+            }
+            __syncthreads();
+            for (uint32_t t = 0; t < h.nterms; t++) {
+                const int64_t k = (int64_t)h.term0 + t;
+                const uint4 *src = reinterpret_cast<const uint4 *>(q.fac + (size_t)k * q.facw);
+                uint32_t fwd[NW];
+                { const uint4 a = __ldg(src); fwd[0] = a.x; fwd[1] = a.y; fwd[2] = a.z; fwd[3] = a.w; }
+                if constexpr (BIG) { const uint4 b = __ldg(src + 1); fwd[4] = b.x; fwd[5] = b.y; fwd[6] = b.z; fwd[7] = b.w; }
+                if (vecs || q.ncomp == 0) {
+                    // plain values: the compact factors (row 0 pads with 1.0, exact)
+                    double b = rows[(size_t)fac_slot(fwd, 0) * kP + lane];
+#pragma unroll
+                    for (int m = 1; m < 2 * NW; m++) if (m < q.nf) b = b * rows[(size_t)fac_slot(fwd, m) * kP + lane];
+#pragma unroll
+                    for (int i = 0; i < kMaxItems; i++) {
+                        const int item = w + i * kWarps;
+                        if (item < n_items) {
+                            if (!vecs) {
+                                const double th = q.theta[k];
+                                s[i][0] = k == 0 ? th * b : s[i][0] + th * b;
+                            } else {
+                                const double *tk = q.theta + (size_t)k * q.nvec + item * 8;
+#pragma unroll
+                                for (int v = 0; v < 8; v++)
+                                    if (item * 8 + v < q.nvec) s[i][v] = k == 0 ? tk[v] * b : s[i][v] + tk[v] * b;
+                            }
+                        }
+                    }
+                } else {
+                    const double th = q.theta[k];
+#pragma unroll
+                    for (int i = 0; i < kMaxItems; i++) {
+                        const int cc = w + i * kWarps;
+                        if (cc < n_items) {
+                            double b = rows[((size_t)fac_slot(fwd, 0) * JW + q.orders[cc][0]) * kP + lane];
+#pragma unroll
+                            for (int j = 1; j < 2 * NW; j++) if (j < d) b = b * rows[((size_t)fac_slot(fwd, j) * JW + q.orders[cc][j]) * kP + lane];
+                            s[i][0] = k == 0 ? th * b : s[i][0] + th * b;
+                        }
+                    }
+                }
+            }
+        }
+        if (p0 + lane < q.n) {
+#pragma unroll
+            for (int i = 0; i < kMaxItems; i++) {
+                const int item = w + i * kWarps;
+                if (item < n_items) {
+                    if (!vecs) q.out[(size_t)(p0 + lane) * q.E + item] = s[i][0];
+                    else {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) if (item * 8 + v < q.nvec) q.out[(size_t)(p0 + lane) * q.nvec + item * 8 + v] = s[i][v];
+                    }
+                }
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -408,7 +530,22 @@ void smolyak_tile_basis_forget(const sk_plan *plan) {
     }
 }
 
+
+// exact-mode linear_combination for any basis size; false if the request is outside what the kernel's per-warp item
+// table holds (more than 64 components or 512 coefficient vectors)
+bool smolyak_tile_lincomb_supported(const sk_plan &plan, int nvec) {
+    if (plan.basis.kind != SK_BASIS_SMOLYAK) return false;
+    return nvec > 1 ? (plan.ncomp == 0 && nvec <= 8 * kMaxItems * kWarps) : plan.E <= kMaxItems * kWarps;
+}
+cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, int64_t ld, cudaStream_t stream);
+cudaError_t smolyak_tile_lincomb_exact(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, cudaStream_t stream) {
+    return smolyak_tile_basis_at_impl(plan, theta, nvec, x, n, out, n, stream);
+}
 cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld, cudaStream_t stream) {
+    return smolyak_tile_basis_at_impl(plan, nullptr, 1, x, n, out, ld, stream);
+}
+// theta == nullptr: basis_at (TMA tiles); otherwise the bit-identical linear combination with the same tables
+cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, int64_t ld, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const int d = plan.basis.d, E = plan.E;
     int jw = 1;
@@ -468,6 +605,28 @@ cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t 
     }
     for (int c = 0; c < plan.ncomp; c++) for (int j = 0; j < d; j++) q.orders[c][j] = (int8_t)plan.orders[c][j];
     q.pb = pb; q.substride = substride;
+    q.theta = theta; q.nvec = nvec;
+    if (theta) {
+        const size_t rows_b = ((size_t)q.max_rows * JW * kP * 8 + 127) & ~(size_t)127;
+        const size_t smem_l = xj_bytes + rows_b;
+        const int64_t tiles_l = (n + kP - 1) / kP;
+        cudaError_t el = cudaSuccess;
+#define SK_LAUNCH_TL(J, G)                                                                                                \
+    do {                                                                                                                  \
+        el = cudaFuncSetAttribute(smolyak_tile_lincomb_kernel<J, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l); \
+        int per_sm = 1;                                                                                                   \
+        if (el == cudaSuccess) el = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smolyak_tile_lincomb_kernel<J, G>, kP * kWarps, smem_l); \
+        const int grid = (int)std::min<int64_t>(tiles_l, (int64_t)sm_count() * std::max(per_sm, 1));                      \
+        if (el == cudaSuccess) smolyak_tile_lincomb_kernel<J, G><<<grid, kP * kWarps, smem_l, stream>>>(q);               \
+    } while (0)
+#define SK_LAUNCH_TLJ(J) do { if (q.facw > 8) SK_LAUNCH_TL(J, true); else SK_LAUNCH_TL(J, false); } while (0)
+        if (JW == 1) SK_LAUNCH_TLJ(1); else if (JW == 2) SK_LAUNCH_TLJ(2); else if (JW == 3) SK_LAUNCH_TLJ(3); else SK_LAUNCH_TLJ(6);
+#undef SK_LAUNCH_TLJ
+#undef SK_LAUNCH_TL
+        if (el != cudaSuccess) return el;
+        count_launch();
+        return cudaGetLastError();
+    }
     static const int no_tma = [] { const char *e = getenv("SK_BASIS_NO_TMA"); return e ? atoi(e) : 0; }();
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof tmap);

@@ -23,6 +23,9 @@ cudaError_t smolyak_direct_basis_at(const sk_plan &plan, const double *x, int64_
 // ---- Smolyak basis_at / collocation_matrix: chunked tables, TMA tensor-map stores (sk_basis.cu); any basis, any ∂ request
 cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t n, double *out, int64_t ld, cudaStream_t stream);
 void smolyak_tile_basis_forget(const sk_plan *plan);
+// bit-identical linear_combination (reference order) on the same chunked tables: any basis size
+bool smolyak_tile_lincomb_supported(const sk_plan &plan, int nvec);
+cudaError_t smolyak_tile_lincomb_exact(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, cudaStream_t stream);
 
 // ---- Smolyak, nested run-structured evaluation (values, or value + full gradient)
 bool smolyak_nested_supported(const sk_plan &plan);

@@ -254,22 +254,20 @@ def test_smolyak_exact_bit_identical(orc, code, d, B, M):
                     orc.smolyak_lincomb(code, d, B, M, theta, x, spec=ospec))
 
 
-def test_smolyak_exact_mode_table_limit_is_reported(orc):
-    # the bit-identical direct kernels hold d·ℓ(B)·(order+1) doubles per point for 32 points in shared memory; a basis
-    # beyond that (InteriorGrid, B = 4: ℓ = 81, six dimensions, gradient) is refused with a clear error, not a CUDA
-    # launch failure, and the fast path still serves it within tolerance
+def test_smolyak_exact_mode_has_no_table_limit(orc):
+    # round 1 refused bit-identical evaluation of bases whose full tables (d·ℓ(B)·(order+1) doubles per point for 32
+    # points) exceed shared memory — InteriorGrid, B = 4: ℓ = 81, six dimensions, gradient.  The chunked-table kernel
+    # serves them in the reference's order; the fast path stays within tolerance
     code, d, B = 0, 6, 4
     basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
     rng = np.random.default_rng(99)
     theta = rng.standard_normal(sk.dimension(basis))
     x = rand_pm1(rng, (50, d))
-    with pytest.raises(sk.UnsupportedError):
-        sk.linear_combination(basis, theta, sk.gradient(d)(x), exact=True)
     ospec = orc.gradient_spec(d)
     want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
+    assert same(sk.linear_combination(basis, theta, sk.gradient(d)(x), exact=True), want)
     scale = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec, absmode=True)
     assert within(sk.linear_combination(basis, theta, sk.gradient(d)(x)), want, scale)
-    # values only need a third of the table: still bit-identical
     assert same(sk.linear_combination(basis, theta, x, exact=True), orc.smolyak_lincomb(code, d, B, B, theta, x)[:, 0])
 
 
@@ -889,3 +887,27 @@ def test_uni_constant_bank_slots_shared_between_derivative_orders(orc):
     torch.cuda.synchronize()
     assert all(torch.equal(o, want0) for o in outs0)
     assert all(torch.equal(o, want1) for o in outs1)
+
+
+def test_exact_mode_for_bases_beyond_shared_memory_tables(orc):
+    """SK_MODE_EXACT for bases whose full tables exceed shared memory (round 1 returned SK_ERR_UNSUPPORTED): the
+    chunked-table kernel keeps the reference's sequential s = s + θ_k·b_k (generic_api.jl:114-128) and is bit-identical."""
+    rng = np.random.default_rng(909)
+    for code, d, B, n, tr in [(0, 6, 4, 41, False), (2, 12, 3, 35, False), (0, 3, 5, 50, True)]:
+        basis0 = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+        K = sk.dimension(basis0)
+        trs_sk = trs_or = None
+        basis = basis0
+        if tr:
+            trs_sk = [sk.BoundedLinear(-1, 2), sk.SemiInfRational(0.5, 2.0), sk.InfRational(0.0, 1.5)]
+            trs_or = [orc.BoundedLinear(-1, 2), orc.SemiInfRational(0.5, 2.0), orc.InfRational(0.0, 1.5)]
+            basis = basis0 @ sk.coordinate_transformations(*trs_sk)
+        u = np.clip((rng.random((n, d)) - 0.5) * 2.2, -0.97, 0.97)
+        y = orc.transform_from_batch(trs_or, u) if tr else u
+        theta = rng.standard_normal(K)
+        assert same(np.asarray(sk.linear_combination(basis, theta, y, exact=True)), orc.smolyak_lincomb(code, d, B, B, theta, y, trs=trs_or)[:, 0])
+        want = orc.smolyak_lincomb(code, d, B, B, theta, y, trs=trs_or, spec=orc.gradient_spec(d))
+        assert same(np.asarray(sk.linear_combination(basis, theta, sk.gradient(d)(y), exact=True)), want)
+        # SVector coefficients (values only), 11 vectors: two groups of 8
+        th = rng.standard_normal((K, 11))
+        assert same(np.asarray(sk.linear_combination(basis, th, y, exact=True)), orc.smolyak_lincomb(code, d, B, B, th, y, trs=trs_or))
