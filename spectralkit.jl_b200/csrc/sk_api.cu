@@ -380,6 +380,9 @@ static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *t
         p->fast_kernel = skk::smolyak_leaf_supported(*p) ? 2 : skk::smolyak_nested_supported(*p) ? 1 : 0;
         // any ∂ request no specialised kernel serves (general specifications; gradients with M < B or d > 10 that neither
         // the leaf nor the run-program kernel takes) goes to the general nested kernel when its state fits
+        // ∂ requests of total order <= 2 (Hessian entries, diagonals, cross partials) on a basis that is one leaf: unrolled
+        // second-order-jet leaves (SK_NO_JET=1 keeps them on the general kernel: experiments)
+        if (p->ncomp > 0 && p->fast_mode < 0 && getenv("SK_NO_JET") == nullptr && skk::smolyak_jet_supported(*p)) p->fast_kernel = 4;
         if (!p->fast_kernel && p->ncomp > 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
         // gradients the leaf kernel cannot serve (block cap M < B, θ too large): the generic nested kernel keeps its state
         // in registers, which spill beyond 8 dimensions (d = 10, B = 3: 3.6 vs 8.9 Mpoints/s); the general kernel keeps it
@@ -387,11 +390,11 @@ static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *t
         if (p->fast_kernel == 1 && p->fast_mode == 1 && d >= 9 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
         {   // experiments: SK_FORCE_GENERAL=1 sends every ∂ request the general kernel can serve to it
             static const int force = [] { const char *e = getenv("SK_FORCE_GENERAL"); return e ? atoi(e) : 0; }();
-            if (force && p->ncomp > 0 && skk::smolyak_general_supported(*p)) p->fast_kernel = 3;
+            if (force && p->ncomp > 0 && skk::smolyak_general_supported(*p)) { p->fast_kernel = 3; p->jet_mode = 0; }
         }
         p->n_runs = (int64_t)p->set.run_len.size();
         p->flops_fast = p->fast_kernel == 2 ? skk::smolyak_leaf_flops(*p) : p->fast_kernel == 1 ? skk::smolyak_nested_flops(*p)
-                        : p->fast_kernel == 3 ? skk::smolyak_general_flops(*p) : p->flops_direct;
+                        : p->fast_kernel == 3 ? skk::smolyak_general_flops(*p) : p->fast_kernel == 4 ? skk::smolyak_jet_flops(*p) : p->flops_direct;
     }
     // the reference throws for order >= 2 through the rational maps (transformations.jl:266,332)
     for (int j = 0; j < d; j++)
@@ -436,6 +439,13 @@ static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *t
             if (!skk::smolyak_general_tree(*p, tree, p->tree_lvl)) SK_FAIL(SK_ERR_ARGUMENT, "internal error: prefix tree");
             CK(cudaMalloc(&p->d_tree, tree.size() * sizeof(uint16_t)));
             CK(cudaMemcpy(p->d_tree, tree.data(), tree.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        }
+        if (p->fast_kernel == 4) {
+            std::vector<uint32_t> thmap;
+            p->theta_slots = skk::smolyak_jet_theta_map(*p, &thmap);
+            if ((int64_t)thmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
+            CK(cudaMalloc(&p->d_thmap, thmap.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(p->d_thmap, thmap.data(), thmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         if (p->fast_kernel == 2) {
             std::vector<uint32_t> units;
@@ -528,6 +538,10 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
     // a few coefficient vectors: one unrolled-leaf launch per vector beats the 8-wide DMMA tile (values only)
     if (!exact && plan->fast_kernel == 2 && (nvec == 1 || (nvec <= leaf_per_vector_max() && plan->fast_mode == 0))) {
         CK(skk::smolyak_leaf_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    if (!exact && nvec == 1 && plan->fast_kernel == 4) {
+        CK(skk::smolyak_jet_lincomb(*plan, d_theta, d_x, n, d_out, stream));
         return SK_OK;
     }
     if (!exact && nvec == 1 && plan->fast_kernel == 3) {

@@ -93,7 +93,10 @@ struct sk_plan {
     int bprog_F = 0, bprog_HL = 0;
     uint16_t *d_tree = nullptr;  // prefix tree of the component table (general nested kernel)
     std::vector<int> tree_lvl;   // first prefix of every level, then the total
-    int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves, 3 general nested (any ∂ spec)
+    int jet_mode = 0;            // second-order-jet leaf kernel (sk_jet.cu): 2 value/gradient/diagonal, 3 full Hessian jet
+    int8_t jet_col[32]{};        // jet component -> output column (-1: not requested)
+    int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves, 3 general nested (any ∂ spec),
+                                 // 4 second-order-jet leaves (∂ requests of total order <= 2 on one-leaf bases)
     double flops_fast = 0, flops_direct = 0;
     // host-buffer staging pool (the only mutable state of a plan; guarded by ws_mu)
     mutable std::mutex ws_mu;

@@ -43,6 +43,16 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int n
                                  double *out, cudaStream_t stream);
 double smolyak_leaf_flops(const sk_plan &plan);
 
+// shared-memory slot of every coefficient of Leaf<T, R> under the layout of leaf_end (sk_leaf_impl.cuh); returns the next slot
+int smolyak_leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
+                         std::vector<uint32_t> *map);
+
+// ---- Smolyak, second-order jets on unrolled leaves (sk_jet.cu): ∂ requests of total order <= 2 on bases that are one leaf
+bool smolyak_jet_supported(sk_plan &plan);       // also fixes plan.jet_mode / plan.jet_col
+int64_t smolyak_jet_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);
+cudaError_t smolyak_jet_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n, double *out, cudaStream_t stream);
+double smolyak_jet_flops(const sk_plan &plan);
+
 // ---- Smolyak, nested evaluation for any ∂ specification with per-coordinate orders <= 2 (sk_general.cu)
 bool smolyak_general_supported(const sk_plan &plan);
 bool smolyak_general_tree(const sk_plan &plan, std::vector<uint16_t> &tree, std::vector<int> &lvl_off);

@@ -32,15 +32,15 @@ static int leaf_depth(const sk_plan &plan) { return plan.leaf_LL; }
 
 // shared-memory slot of every coefficient: mirrors leaf_end / LeafBlocks of sk_leaf_impl.cuh (pair-aligned blocks
 // wherever a runtime loop changes the base); returns the slot after the last coefficient of Leaf<T, R>
-static int leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
-                        std::vector<uint32_t> *map) {
+int smolyak_leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
+                         std::vector<uint32_t> *map) {
     if (T == 0 || R == 0) { if (map) map->push_back((uint32_t)(base + off)); return off + 1; }
-    off = leaf_map_rec(S, blk_of, LOOPD, T - 1, R, off, base, map);
+    off = smolyak_leaf_map_rec(S, blk_of, LOOPD, T - 1, R, off, base, map);
     if (T < LOOPD) {
         for (int64_t i = 2; i <= S.ell[(size_t)R]; i++) {
             const int b = blk_of[(size_t)i];
             if (R - b == 0) { if (map) map->push_back((uint32_t)(base + off)); off++; }
-            else off = leaf_map_rec(S, blk_of, LOOPD, T - 1, R - b, off, base, map);
+            else off = smolyak_leaf_map_rec(S, blk_of, LOOPD, T - 1, R - b, off, base, map);
         }
     } else {
         for (int B = 1; B <= R; B++) {
@@ -50,8 +50,8 @@ static int leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of
                 off = even_up(off + cnt);
             } else {
                 const int start = even_up(off);
-                const int CS = even_up(leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, 0, nullptr));
-                if (map) for (int c = 0; c < cnt; c++) leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, base + start + (int64_t)c * CS, map);
+                const int CS = even_up(smolyak_leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, 0, nullptr));
+                if (map) for (int c = 0; c < cnt; c++) smolyak_leaf_map_rec(S, blk_of, LOOPD, T - 1, R - B, 0, base + start + (int64_t)c * CS, map);
                 off = start + cnt * CS;
             }
         }
@@ -77,7 +77,7 @@ int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) 
     smolyak_leaf_units(plan, units);
     if (map) { map->clear(); map->reserve((size_t)S.K); }
     int64_t pos = 0;
-    for (uint32_t w : units) pos += even_up(leaf_map_rec(S, blk_of, LOOPD, LL, (int)(w & 0xFF), 0, pos, map));
+    for (uint32_t w : units) pos += even_up(smolyak_leaf_map_rec(S, blk_of, LOOPD, LL, (int)(w & 0xFF), 0, pos, map));
     return pos;
 }
 

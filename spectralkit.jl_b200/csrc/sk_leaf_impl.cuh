@@ -618,9 +618,29 @@ constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
     const int t = (R >= 4 || (R == 3 && (grad || gk == SK_GRID_INTERIOR))) ? 2 : leaf_treg_c(LL, grad);
     return LL < t ? LL : t;
 }
+// the largest single leaves (2 641..10 625 terms): their straight-line code is several hundred KB when only the top
+// dimension is looped, far beyond the instruction cache, so the gradient kernels of InteriorGrid / InteriorGrid2 loop
+// dimensions 4.. (+24..59 %; the EndpointGrid ones and all values-only kernels lose 15..45 % by it and stay as they were:
+// profiles/r2_big_leaves.md).  SK_BIG_LOOPD_G / _V: first looped dimension for gradients / values (experiments)
+#ifndef SK_BIG_LOOPD_G
+#define SK_BIG_LOOPD_G 4
+#endif
+#ifndef SK_BIG_LOOPD_V
+#define SK_BIG_LOOPD_V 99
+#endif
+constexpr bool leaf_single_big_c(int gk, int LL, int R) {
+    return (LL == 5 || LL == 6) && ((gk == SK_GRID_INTERIOR && R == 4) || (gk == SK_GRID_INTERIOR2 && R == 5));
+}
 // first looped dimension; the host's coefficient layout (smolyak_leaf_theta_map) follows it
 constexpr int leaf_single_loopd_c(int gk, int LL, int R, bool grad) {
-    return leaf_single_looped_c(gk, LL, R) ? leaf_single_treg_c(gk, LL, R, grad) + 1 : leaf_loopd_c(LL, grad);
+    if (leaf_single_looped_c(gk, LL, R)) return leaf_single_treg_c(gk, LL, R, grad) + 1;
+    const int base = leaf_loopd_c(LL, grad);
+    if (leaf_single_big_c(gk, LL, R)) {
+        const int lo = leaf_single_treg_c(gk, LL, R, grad) + 1, want = grad ? SK_BIG_LOOPD_G : SK_BIG_LOOPD_V;
+        const int v = want < lo ? lo : want;
+        return v < base ? v : base;
+    }
+    return base;
 }
 #ifdef SK_SINGLE_HEADLINE
 constexpr int leaf_single_nt_c(int gk, int LL, int R, bool grad) { return gk == SK_GRID_INTERIOR2 && LL == 6 && R == 4 ? leaf_nt_c(LL, grad) : 256; }

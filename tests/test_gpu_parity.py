@@ -444,23 +444,26 @@ def test_smolyak_svector_coefficients(orc):
 
 
 # ---- general ∂ specifications through the fast general nested kernel (fast_path 3)
-@pytest.mark.parametrize("code,d,B,parts", [
-    (2, 2, 3, [(1, 1)]),                                  # test/test_smolyak.jl:39: ∂(1, 1) → [f, ∂1, ∂2, ∂1∂2]
-    (0, 3, 3, [(1, 1), (0, 2)]),
-    (1, 4, 3, [(2,), (0, 2), (0, 0, 2), (0, 0, 0, 2)]),   # value + diagonal of the Hessian
-    (2, 6, 4, [(1, 1), (0, 1, 1), (0, 0, 0, 2, 1), (1, 0, 0, 0, 0, 1)]),
-    (2, 3, 4, [(2, 2, 2)]),                               # every order up to 2 in every coordinate: 27 components
-    (2, 1, 4, [(2,)]),
-    (2, 8, 3, [(0, 0, 0, 0, 0, 0, 1, 1), (2,)]),
+# Requests whose components all have total order <= 2 on a basis that is one leaf (d <= 6) take the second-order-jet
+# leaves (fast_path 4, sk_jet_impl.cuh); everything else the general nested kernel (fast_path 3).
+@pytest.mark.parametrize("code,d,B,parts,path", [
+    (2, 2, 3, [(1, 1)], 4),                                  # test/test_smolyak.jl:39: ∂(1, 1) → [f, ∂1, ∂2, ∂1∂2]
+    (0, 3, 3, [(1, 1), (0, 2)], 4),
+    (1, 4, 3, [(2,), (0, 2), (0, 0, 2), (0, 0, 0, 2)], 4),   # value + diagonal of the Hessian
+    (2, 6, 4, [(1, 1), (0, 1, 1), (0, 0, 0, 2, 1), (1, 0, 0, 0, 0, 1)], 3),   # a third-order component
+    (2, 3, 4, [(2, 2, 2)], 3),                               # every order up to 2 in every coordinate: 27 components
+    (2, 1, 4, [(2,)], 4),
+    (2, 8, 3, [(0, 0, 0, 0, 0, 0, 1, 1), (2,)], 3),          # more than six dimensions
+    (0, 6, 4, [(1, 1), (0, 0, 2)], 3),                       # 4 361 terms: no jet leaf of that size is built
 ])
-def test_smolyak_general_spec_fast(orc, code, d, B, parts):
+def test_smolyak_general_spec_fast(orc, code, d, B, parts, path):
     rng = np.random.default_rng(4242 + d + B)
     basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
     spec = sk.partial(*parts[0])
     for q in parts[1:]:
         spec = spec | sk.partial(*q)
     ospec = orc.deriv_spec(parts, d)
-    assert sk.get_plan(basis, 0, spec).info.fast_path == 3
+    assert sk.get_plan(basis, 0, spec).info.fast_path == path
     theta = rng.standard_normal(sk.dimension(basis))
     x = rand_pm1(rng, (333, d))
     want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
@@ -468,6 +471,70 @@ def test_smolyak_general_spec_fast(orc, code, d, B, parts):
     got = sk.linear_combination(basis, theta, spec(x))
     assert got.shape == want.shape and within(got, want, scale)
     assert same(sk.linear_combination(basis, theta, spec(x), exact=True), want)
+
+
+def hessian_parts(d, diag_only=False):
+    """∂ requests whose union is the Hessian (with its lower orders: value and gradient) or its diagonal"""
+    parts = []
+    for n in range(d):
+        for m in range(n + 1):
+            if diag_only and m != n:
+                continue
+            o = [0] * (n + 1)
+            o[m] += 1
+            o[n] += 1
+            parts.append(tuple(o))
+    return parts
+
+
+@pytest.mark.parametrize("code,d,B", [
+    (0, 1, 4), (0, 2, 4), (0, 3, 3), (0, 4, 4), (0, 5, 3), (0, 6, 3),
+    (1, 1, 5), (1, 2, 5), (1, 3, 4), (1, 4, 2), (1, 5, 4), (1, 6, 4),
+    (2, 1, 5), (2, 2, 5), (2, 3, 5), (2, 4, 4), (2, 5, 4), (2, 6, 4), (2, 6, 1), (2, 4, 5),
+])
+@pytest.mark.parametrize("diag", [False, True])
+def test_smolyak_second_order_jet_leaves(orc, code, d, B, diag):
+    # full Hessian jets (value, gradient, all second partials: 28 components at d = 6) and their diagonal variants
+    # through smolyak_jet_kernel, against the oracle's direct evaluation (derivatives.jl:502-511)
+    rng = np.random.default_rng(7000 + 100 * code + 10 * d + B)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    parts = hessian_parts(d, diag)
+    spec = sk.partial(*parts[0])
+    for q in parts[1:]:
+        spec = spec | sk.partial(*q)
+    ospec = orc.deriv_spec(parts, d)
+    info = sk.get_plan(basis, 0, spec).info
+    assert info.fast_path == 4 and info.E == (2 * d + 1 if diag else (d + 1) * (d + 2) // 2)
+    theta = rng.standard_normal(sk.dimension(basis))
+    x = rand_pm1(rng, (161, d))
+    want = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec)
+    scale = orc.smolyak_lincomb(code, d, B, B, theta, x, spec=ospec, absmode=True)
+    got = sk.linear_combination(basis, theta, spec(x))
+    assert got.shape == want.shape and within(got, want, scale)
+
+
+def test_smolyak_second_order_jet_subsets_and_transformations(orc):
+    # a request that names only some second partials stores only those columns, in the request's canonical order; mixed
+    # transformations (second derivatives through the rational maps are the opt-in extension, SURVEY.md Appendix A.3)
+    rng = np.random.default_rng(7777)
+    d, B = 6, 4
+    trs = [mk_tr(orc, k, a, b) for k, a, b in MIXED6]
+    ct = sk.coordinate_transformations(*[t[0] for t in trs])
+    otr = [t[1] for t in trs]
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    theta = rng.standard_normal(sk.dimension(basis))
+    y = sk.transform_from(basis, ct, rng.uniform(-0.95, 0.95, (150, d)))
+    for parts in ([(1, 0, 0, 0, 0, 1)], [(0, 0, 2), (0, 1, 0, 1)], [(2,), (0, 0, 0, 0, 0, 2)], hessian_parts(d)):
+        spec = sk.partial(*parts[0])
+        for q in parts[1:]:
+            spec = spec | sk.partial(*q)
+        ospec = orc.deriv_spec(parts, d)
+        assert sk.get_plan(basis @ ct, 0, spec, allow_rational_d2=True).info.fast_path == 4
+        want = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec, ext2=True)
+        scale = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=otr, spec=ospec, ext2=True, absmode=True)
+        got = sk.linear_combination(basis @ ct, theta, spec(y), allow_rational_d2=True)
+        assert got.shape == want.shape and within(got, want, scale)
+        assert same(sk.linear_combination(basis @ ct, theta, spec(y), allow_rational_d2=True, exact=True), want)
 
 
 def test_smolyak_general_spec_fast_transformed(orc):
