@@ -165,11 +165,13 @@ __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.s
 //   other ∂ plans: all d factors of every component, left to right
 // rows_s: shared address of the rows + this lane's offset; st_s: shared address of this lane's slot in term 0 of the
 // staging tile, tstride: bytes between consecutive terms there
-template <int JW, int TW, bool BIG, int GD>
+template <int JW, int TW, bool BIG, int GD, int PPL>
 __device__ __forceinline__ void tile_products(const BasisParams &q, uint32_t rows_s, const uint4 *fw, uint32_t st_s, uint32_t tstride) {
     const int E = q.E, d = q.d;
     constexpr int NW = BIG ? 8 : 4, NS = 2 * NW;      // factor words / slots per term (d <= 8: four words)
-    constexpr uint32_t ROWB = (uint32_t)JW * kP * 8;  // bytes per table row
+    constexpr int P = kP * PPL;                       // points per CTA: PPL per lane (lane, lane + 32)
+    constexpr uint32_t ROWB = (uint32_t)JW * P * 8;   // bytes per table row
+    static_assert(PPL == 1 || (JW == 1 && GD == 0), "two points per lane: plain values only");
     // every lane holds the factor words of term `lane` of the tile (lanes >= TW: unused); broadcast term by term.  Two words
     // (four slots) cover values-only plans with B <= 4 and ∂ plans with d <= 4: the rest sits behind one uniform branch
     const int nwords = q.ncomp == 0 ? (q.nf + 1) >> 1 : (d + 1) >> 1;
@@ -196,22 +198,42 @@ __device__ __forceinline__ void tile_products(const BasisParams &q, uint32_t row
 #pragma unroll
     for (int t = 0; t < TW; t++) dst[t] = st_s + (uint32_t)t * tstride;
     if (q.ncomp == 0) {
-        double b[TW];
+        // the PPL points of a lane (lane, lane + 32: 256 bytes apart in every row and in the staging tile) share the
+        // factor words and every address computation — 40 % of the instructions of the one-point version
+        double b[TW][PPL];
 #pragma unroll
-        for (int t = 0; t < TW; t++) b[t] = lds64(rows_s + fac_slot(w[t], 0) * ROWB);
+        for (int t = 0; t < TW; t++) {
+            const uint32_t a0 = rows_s + fac_slot(w[t], 0) * ROWB;
 #pragma unroll
-        for (int t = 0; t < TW; t++) b[t] = b[t] * lds64(rows_s + fac_slot(w[t], 1) * ROWB);      // padding = row 0 = 1.0: exact
+            for (int pp = 0; pp < PPL; pp++) b[t][pp] = lds64(a0 + 256u * pp);
+        }
+#pragma unroll
+        for (int t = 0; t < TW; t++) {
+            const uint32_t a1 = rows_s + fac_slot(w[t], 1) * ROWB;      // padding = row 0 = 1.0: exact
+#pragma unroll
+            for (int pp = 0; pp < PPL; pp++) b[t][pp] = b[t][pp] * lds64(a1 + 256u * pp);
+        }
 #pragma unroll
         for (int m = 2; m < NS; m += 2) {
             if (m < q.nf) {
 #pragma unroll
-                for (int t = 0; t < TW; t++) b[t] = b[t] * lds64(rows_s + fac_slot(w[t], m) * ROWB);
+                for (int t = 0; t < TW; t++) {
+                    const uint32_t am = rows_s + fac_slot(w[t], m) * ROWB;
 #pragma unroll
-                for (int t = 0; t < TW; t++) b[t] = b[t] * lds64(rows_s + fac_slot(w[t], m + 1) * ROWB);
+                    for (int pp = 0; pp < PPL; pp++) b[t][pp] = b[t][pp] * lds64(am + 256u * pp);
+                }
+#pragma unroll
+                for (int t = 0; t < TW; t++) {
+                    const uint32_t am = rows_s + fac_slot(w[t], m + 1) * ROWB;
+#pragma unroll
+                    for (int pp = 0; pp < PPL; pp++) b[t][pp] = b[t][pp] * lds64(am + 256u * pp);
+                }
             }
         }
 #pragma unroll
-        for (int t = 0; t < TW; t++) sts64(dst[t], b[t]);
+        for (int t = 0; t < TW; t++)
+#pragma unroll
+            for (int pp = 0; pp < PPL; pp++) sts64(dst[t] + 256u * pp, b[t][pp]);
     } else if constexpr (GD > 0) {
         // rows_s already points at this lane's (T, T') pair: [row][lane] double2
 #pragma unroll
@@ -241,13 +263,13 @@ __device__ __forceinline__ void tile_products(const BasisParams &q, uint32_t row
         }
         for (int cc = 0; cc < E; cc++) {
             double b[TW];
-            const uint32_t o0 = (uint32_t)q.orders[cc][0] * (kP * 8);
+            const uint32_t o0 = (uint32_t)q.orders[cc][0] * (P * 8);
 #pragma unroll
             for (int t = 0; t < TW; t++) b[t] = lds64(ra[t][0] + o0);
 #pragma unroll
             for (int j = 1; j < NS; j++) {
                 if (j < d) {
-                    const uint32_t o = (uint32_t)q.orders[cc][j] * (kP * 8);
+                    const uint32_t o = (uint32_t)q.orders[cc][j] * (P * 8);
 #pragma unroll
                     for (int t = 0; t < TW; t++) b[t] = b[t] * lds64(ra[t][j] + o);
                 }
@@ -259,37 +281,43 @@ __device__ __forceinline__ void tile_products(const BasisParams &q, uint32_t row
 }
 
 // shared memory: [x jets d·JW·32][rows max_rows·JW·32][staging kWarps·2·tw·32·E], 128-byte aligned pieces
-template <int JW, int TW, bool BIG, int GD>
+template <int JW, int TW, bool BIG, int GD, int PPL>
 __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_kernel(const __grid_constant__ BasisParams q,
                                                                           const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int d = q.d, E = q.E;
-    double *xj = reinterpret_cast<double *>(smem_raw);                                  // [d][JW][32]
-    const size_t xj_bytes = ((size_t)d * JW * kP * 8 + 127) & ~(size_t)127;
-    double *rows = reinterpret_cast<double *>(smem_raw + xj_bytes);                     // [row][JW][32]
-    const size_t rows_bytes = ((size_t)q.max_rows * JW * kP * 8 + 127) & ~(size_t)127;
-    const size_t tile_bytes = ((size_t)(kP / q.pb) * q.substride * 8 + 127) & ~(size_t)127;
+    constexpr int P = kP * PPL;                                                         // points per CTA (PPL per lane)
+    double *xj = reinterpret_cast<double *>(smem_raw);                                  // [d][JW][P]
+    const size_t xj_bytes = ((size_t)d * JW * P * 8 + 127) & ~(size_t)127;
+    double *rows = reinterpret_cast<double *>(smem_raw + xj_bytes);                     // [row][JW][P]
+    const size_t rows_bytes = ((size_t)q.max_rows * JW * P * 8 + 127) & ~(size_t)127;
+    const size_t tile_bytes = ((size_t)(P / q.pb) * q.substride * 8 + 127) & ~(size_t)127;
     double *stage = reinterpret_cast<double *>(smem_raw + xj_bytes + rows_bytes + (size_t)w * 2 * tile_bytes);
-    const int nsub = kP / q.pb;                                                         // TMA boxes per tile along the points
+    const int nsub = P / q.pb;                                                          // TMA boxes per tile along the points
     // this lane's slot in term 0 of a staging tile ([sub-box][term][point in box][component]) and the stride between terms
     const uint32_t lane_off = (uint32_t)((lane / q.pb) * q.substride + (lane % q.pb) * E) * 8u, tstride = (uint32_t)(q.pb * E) * 8u;
     int buf = 0;
 
-    for (int64_t p0 = (int64_t)blockIdx.x * kP; p0 < q.n; p0 += (int64_t)gridDim.x * kP) {
-        const int64_t p = min(p0 + lane, q.n - 1);
+    for (int64_t p0 = (int64_t)blockIdx.x * P; p0 < q.n; p0 += (int64_t)gridDim.x * P) {
         __syncthreads();                                            // previous tile's rows and jets are no longer read
         for (int j = w; j < d; j += kWarps) {
-            double v[JW];
-            skd::to_pm1_jet<JW>(q.tr[j], __ldcs(q.x + p * d + j), v);
 #pragma unroll
-            for (int r = 0; r < JW; r++) xj[((size_t)j * JW + r) * kP + lane] = v[r];
+            for (int pp = 0; pp < PPL; pp++) {
+                const int64_t p = min(p0 + lane + 32 * pp, q.n - 1);
+                double v[JW];
+                skd::to_pm1_jet<JW>(q.tr[j], __ldcs(q.x + p * d + j), v);
+#pragma unroll
+                for (int r = 0; r < JW; r++) xj[((size_t)j * JW + r) * P + lane + 32 * pp] = v[r];
+            }
         }
         if (w == kWarps - 1) {                                      // row 0: the jet of T_0 = (1, 0, …)
             if constexpr (GD > 0) reinterpret_cast<double2 *>(rows)[lane] = make_double2(1.0, 0.0);
             else {
 #pragma unroll
-                for (int r = 0; r < JW; r++) rows[(size_t)r * kP + lane] = r == 0 ? 1.0 : 0.0;
+                for (int pp = 0; pp < PPL; pp++)
+#pragma unroll
+                    for (int r = 0; r < JW; r++) rows[(size_t)r * P + lane + 32 * pp] = r == 0 ? 1.0 : 0.0;
             }
         }
         for (int c = 0; c < q.n_chunks; c++) {
@@ -301,18 +329,26 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
                 for (int j = 0; j < d; j++) {
                     const int maxidx = bl[0], cnt = bl[1];
                     if (cnt > 0 && (j % kWarps) == w) {
-                        Jet<JW> X, fp = skd::jet_one<JW>(), fpp, f;
+                        Jet<JW> X[PPL], fp[PPL], fpp[PPL], f[PPL];
 #pragma unroll
-                        for (int r = 0; r < JW; r++) { X.c[r] = xj[((size_t)j * JW + r) * kP + lane]; fpp.c[r] = X.c[r]; }
+                        for (int pp = 0; pp < PPL; pp++) {
+                            fp[pp] = skd::jet_one<JW>();
+#pragma unroll
+                            for (int r = 0; r < JW; r++) { X[pp].c[r] = xj[((size_t)j * JW + r) * P + lane + 32 * pp]; fpp[pp].c[r] = X[pp].c[r]; }
+                        }
                         int nx = 0, want = bl[2];
                         for (int i = 2; i <= maxidx; i++) {
-                            f = skd::cheb_step_exact<JW>(X, fp, fpp); fpp = fp; fp = f;
-                            if (i == want) {
-                                if constexpr (GD > 0) reinterpret_cast<double2 *>(rows)[(size_t)bl[3 + 2 * nx] * kP + lane] = make_double2(f.c[0], f.c[JW > 1 ? 1 : 0]);
-                                else {
-                                    double *r0 = rows + (size_t)bl[3 + 2 * nx] * JW * kP + lane;
 #pragma unroll
-                                    for (int r = 0; r < JW; r++) r0[(size_t)r * kP] = f.c[r];
+                            for (int pp = 0; pp < PPL; pp++) { f[pp] = skd::cheb_step_exact<JW>(X[pp], fp[pp], fpp[pp]); fpp[pp] = fp[pp]; fp[pp] = f[pp]; }
+                            if (i == want) {
+                                if constexpr (GD > 0) reinterpret_cast<double2 *>(rows)[(size_t)bl[3 + 2 * nx] * kP + lane] = make_double2(f[0].c[0], f[0].c[JW > 1 ? 1 : 0]);
+                                else {
+#pragma unroll
+                                    for (int pp = 0; pp < PPL; pp++) {
+                                        double *r0 = rows + (size_t)bl[3 + 2 * nx] * JW * P + lane + 32 * pp;
+#pragma unroll
+                                        for (int r = 0; r < JW; r++) r0[(size_t)r * P] = f[pp].c[r];
+                                    }
                                 }
                                 nx++;
                                 want = nx < cnt ? bl[2 + 2 * nx] : 0;
@@ -343,7 +379,7 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
                 double *st = stage + (size_t)buf * (tile_bytes / 8);
                 const int nt = min((uint32_t)TW, h.nterms - s0);
                 const int64_t k0 = (int64_t)h.term0 + s0;
-                tile_products<JW, TW, BIG, GD>(q, (uint32_t)__cvta_generic_to_shared(rows) + (uint32_t)lane * (GD > 0 ? 16u : 8u), fw, (uint32_t)__cvta_generic_to_shared(st) + lane_off, tstride);
+                tile_products<JW, TW, BIG, GD, PPL>(q, (uint32_t)__cvta_generic_to_shared(rows) + (uint32_t)lane * (GD > 0 ? 16u : 8u), fw, (uint32_t)__cvta_generic_to_shared(st) + lane_off, tstride);
                 if (q.use_tma) {
                     proxy_fence();
                     __syncwarp();
@@ -356,7 +392,7 @@ __global__ void __launch_bounds__(kP * kWarps, BIG ? 1 : 2) smolyak_tile_basis_k
                     __syncwarp();
                 } else {
                     __syncwarp();
-                    const int64_t row_elems = (int64_t)kP * E;
+                    const int64_t row_elems = (int64_t)P * E;
                     for (int t = 0; t < nt; t++) {
                         double *g = q.out + ((size_t)(k0 + t) * q.ld + p0) * E;
                         for (int e = lane; e < row_elems; e += 32) {
@@ -511,7 +547,7 @@ EncodeTiledFn encode_tiled() {
 // device-resident chunk programs of a plan, one per jet width, built on first use
 struct ProgramCache {
     std::mutex mu;
-    struct Entry { const sk_plan *plan; int jw, device; BasisProgram host; ChunkHdr *d_hdr; uint16_t *d_build, *d_fac; int tw, row_cap; };
+    struct Entry { const sk_plan *plan; int jw, device, pts; BasisProgram host; ChunkHdr *d_hdr; uint16_t *d_build, *d_fac; int tw, row_cap; };
     std::list<Entry> entries;      // a list: entries keep their address while other threads add theirs
 };
 ProgramCache &cache() { static ProgramCache c; return c; }
@@ -553,25 +589,31 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
     if (plan.ncomp == 0) jw = 1;
     const int JW = jw <= 3 ? jw : 6;
     // staging tile of one warp: TW terms × 32 points × E doubles, 2-4 KB (one 16 KB buffer pair per warp at E = 64)
-    int tw = 8;                                                     // TW terms per warp tile: a power of two, 2-4 KB per tile
+    // plain values (one double per element): two points per lane, 64 per CTA (SK_BASIS_PPL1=1: one; experiments)
+    static const int ppl1 = [] { const char *e = getenv("SK_BASIS_PPL1"); return e ? atoi(e) : 0; }();
+    const bool two = theta == nullptr && plan.ncomp == 0 && E == 1 && JW == 1 && !ppl1;
+    const int P = two ? 2 * kP : kP;
+    int tw = two ? 4 : 8;                                           // TW terms per warp tile: a power of two, 2-4 KB per tile
     while (tw > 1 && tw * E > 16) tw >>= 1;
     // TMA box: pb points × E components per row (<= 256 elements), TW rows; the sub-boxes of a staging tile start on
     // 128-byte boundaries (source alignment of cp.async.bulk.tensor)
-    int pb = kP;
+    int pb = P;
     while (pb * E > 256) pb >>= 1;
     const int substride = (tw * pb * E + 15) & ~15;
-    const size_t tile_bytes = (((size_t)(kP / pb) * substride * 8) + 127) & ~(size_t)127;
-    const size_t xj_bytes = ((size_t)d * JW * kP * 8 + 127) & ~(size_t)127;
+    const size_t tile_bytes = (((size_t)(P / pb) * substride * 8) + 127) & ~(size_t)127;
+    const size_t xj_bytes = ((size_t)d * JW * P * 8 + 127) & ~(size_t)127;
     const size_t stage_bytes = (size_t)kWarps * 2 * tile_bytes;
     const size_t budget = 200 * 1024;
-    if (xj_bytes + stage_bytes + (size_t)(d + 2) * JW * kP * 8 > budget) return cudaErrorInvalidConfiguration;
+    if (xj_bytes + stage_bytes + (size_t)(d + 2) * JW * P * 8 > budget) return cudaErrorInvalidConfiguration;
     // rows: enough for one slice of terms at least; more rows = larger chunks = fewer recurrence re-runs.  Two CTAs per SM
     // when the whole table is small.
-    int row_cap = (int)((budget - xj_bytes - stage_bytes) / ((size_t)JW * kP * 8));
+    int row_cap = (int)((budget - xj_bytes - stage_bytes) / ((size_t)JW * P * 8));
     row_cap = std::min(row_cap, 1 + d * (int)plan.H);
-    const int half_cap = (int)((budget / 2 - xj_bytes - stage_bytes > 0 ? budget / 2 - xj_bytes - stage_bytes : 0) / ((size_t)JW * kP * 8));
+    const int half_cap = (int)((budget / 2 - xj_bytes - stage_bytes > 0 ? budget / 2 - xj_bytes - stage_bytes : 0) / ((size_t)JW * P * 8));
     if (half_cap >= 1 + d * (int)std::min<int64_t>(plan.H, 16)) row_cap = std::min(row_cap, half_cap);
-    row_cap = std::max(row_cap, kWarps * tw * d + 1);
+    // one slice of kWarps·TW terms must fit in any case: every term adds at most d rows (plain values: min(d, B), the
+    // factors with index != 1)
+    row_cap = std::max(row_cap, kWarps * tw * (plan.ncomp == 0 ? std::min(d, plan.basis.B) : d) + 1);
 
     ProgramCache &pc = cache();
     ProgramCache::Entry *en = nullptr;
@@ -579,9 +621,9 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
         std::lock_guard<std::mutex> lk(pc.mu);
         int dev = 0;
         cudaGetDevice(&dev);
-        for (auto &e : pc.entries) if (e.plan == &plan && e.jw == JW && e.device == dev) { en = &e; break; }
+        for (auto &e : pc.entries) if (e.plan == &plan && e.jw == JW && e.device == dev && e.pts == P) { en = &e; break; }
         if (!en) {
-            ProgramCache::Entry e{&plan, JW, dev, {}, nullptr, nullptr, nullptr, tw, row_cap};
+            ProgramCache::Entry e{&plan, JW, dev, P, {}, nullptr, nullptr, nullptr, tw, row_cap};
             build_program(plan.set, plan.ncomp > 0, row_cap, tw, e.host);
             cudaError_t ce = cudaMalloc(&e.d_hdr, e.host.hdr.size() * sizeof(ChunkHdr));
             if (ce == cudaSuccess) ce = cudaMalloc(&e.d_build, std::max<size_t>(2, e.host.build.size() * 2));
@@ -642,24 +684,27 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         q.use_tma = r == CUDA_SUCCESS;
     }
-    const size_t rows_bytes = ((size_t)q.max_rows * JW * kP * 8 + 127) & ~(size_t)127;
+    const size_t rows_bytes = ((size_t)q.max_rows * JW * P * 8 + 127) & ~(size_t)127;
     const size_t smem = xj_bytes + rows_bytes + stage_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    const int64_t tiles = (n + kP - 1) / kP;
+    const int64_t tiles = (n + P - 1) / P;
     cudaError_t e = cudaSuccess;
-#define SK_LAUNCH_TB(J, T, G, D)                                                                                          \
+#define SK_LAUNCH_TBP(J, T, G, D, PL)                                                                                     \
     do {                                                                                                                  \
-        e = cudaFuncSetAttribute(smolyak_tile_basis_kernel<J, T, G, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        e = cudaFuncSetAttribute(smolyak_tile_basis_kernel<J, T, G, D, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         int per_sm = 1;                                                                                                   \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smolyak_tile_basis_kernel<J, T, G, D>, kP * kWarps, smem); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smolyak_tile_basis_kernel<J, T, G, D, PL>, kP * kWarps, smem); \
         const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * std::max(per_sm, 1));                        \
-        if (e == cudaSuccess) smolyak_tile_basis_kernel<J, T, G, D><<<grid, kP * kWarps, smem, stream>>>(q, tmap);        \
+        if (e == cudaSuccess) smolyak_tile_basis_kernel<J, T, G, D, PL><<<grid, kP * kWarps, smem, stream>>>(q, tmap);    \
     } while (0)
+#define SK_LAUNCH_TB(J, T, G, D) SK_LAUNCH_TBP(J, T, G, D, 1)
 #define SK_LAUNCH_TBT(J, G) do { if (tw == 8) SK_LAUNCH_TB(J, 8, G, 0); else if (tw == 4) SK_LAUNCH_TB(J, 4, G, 0); else if (tw == 2) SK_LAUNCH_TB(J, 2, G, 0); else SK_LAUNCH_TB(J, 1, G, 0); } while (0)
 #define SK_LAUNCH_TBJ(J) do { if (q.facw > 8) SK_LAUNCH_TBT(J, true); else SK_LAUNCH_TBT(J, false); } while (0)
     // full gradient [value, ∂1..∂d] (the plan's fast_mode 1) in d <= 8 dimensions: (T, T') rows, shared prefix products
     const bool grad = plan.fast_mode == 1 && JW == 2 && d >= 1 && d <= 8 && tw <= 4;
-    if (grad) {
+    if (two) {
+        if (q.facw > 8) SK_LAUNCH_TBP(1, 4, true, 0, 2); else SK_LAUNCH_TBP(1, 4, false, 0, 2);
+    } else if (grad) {
         switch (d) {
 #define SK_G(D) case D: if (tw == 4) SK_LAUNCH_TB(2, 4, false, D); else if (tw == 2) SK_LAUNCH_TB(2, 2, false, D); else SK_LAUNCH_TB(2, 1, false, D); break;
         SK_G(1) SK_G(2) SK_G(3) SK_G(4) SK_G(5) SK_G(6) SK_G(7) SK_G(8)
@@ -669,6 +714,7 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
 #undef SK_LAUNCH_TBT
 #undef SK_LAUNCH_TBJ
 #undef SK_LAUNCH_TB
+#undef SK_LAUNCH_TBP
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();

@@ -6,9 +6,11 @@
 // pivoting followed by two triangular solves; this file does the same with its own kernels (no cuSOLVER, no cuBLAS):
 //
 //   blocked right-looking LU, panels of NB = 64 columns of the column-major K×K matrix:
-//     lu_panel_kernel    one CTA factors 8 columns of the panel at a time: per column a block-wide arg-max (first maximal
-//                        |a|, as LAPACK's idamax), row swap across the panel, reciprocal scaling, rank-1 update inside
-//                        the 8 columns; lu_panel_update_kernel brings the panel's other columns up to date on all SMs
+//     lu_panel_cluster_kernel  a thread-block cluster of up to 8 CTAs factors 8 columns of the panel at a time with the
+//                        sub-panel in distributed shared memory: per column an arg-max (first maximal |a|, as LAPACK's
+//                        idamax) agreed on through DSMEM, row swap across the panel, reciprocal scaling, rank-1 update
+//                        inside the 8 columns (lu_panel_kernel: the same on global memory, for sub-panels beyond 25 600
+//                        rows); lu_panel_update_kernel brings the panel's other columns up to date on all SMs
 //     lu_swap_kernel     the panel's row interchanges applied to the columns left and right of it
 //     lu_trsm_kernel     U12 = L11⁻¹·A12 (unit lower 64×64 triangle in shared memory, one matrix column per thread)
 //     lu_gemm_kernel     A22 −= L21·U12: the (2/3)·K³ flops of the factorisation, on the FP64 tensor path —
@@ -18,17 +20,32 @@
 //
 // An initialisation-time step, not the hot path; K ≤ 46 340 (the matrix must fit the device).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "sk_launch.h"
 
+namespace cg = cooperative_groups;
 using skh::set_error;
 
 namespace {
 
+// global -> shared copies that do not pass through registers: every thread issues all of its copies, then waits once, so a
+// tile costs ONE memory round trip instead of one per loop iteration (these kernels are latency-bound, not bandwidth-bound)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid = true) {
+    const int sz = valid ? 8 : 0;             // src-size 0: the destination is zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 constexpr int NB = 64;           // panel width
+constexpr int IB = 8;            // sub-panel width
 constexpr int kPitch = 68;       // shared-memory pitch of the GEMM operand tiles (≡ 4 mod 16: conflict-free fragment loads)
 
 // ---- panel factorisation: columns [k0, k0+nb) of rows [k0, K); one CTA of 1024 threads
@@ -110,9 +127,165 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, 
     }
 }
 
+// ---- the same sub-panel factorisation on a thread-block CLUSTER: the ib <= 8 columns of the sub-panel (rows rb..K-1) live
+// in the shared memory of up to 8 CTAs, `slice` rows each, so the per-column steps (arg-max, swap, scaling, rank-1 update)
+// run at shared-memory latency instead of one L2 round trip each — the global-memory kernel above spends 6.6 µs per
+// column.  Per column: every CTA finds the first maximal |a| of its rows and publishes it; after one cluster barrier all
+// CTAs read the candidates through distributed shared memory and agree on the pivot (LAPACK's first-maximum rule); rank 0,
+// which owns the diagonal rows, exchanges the pivot row with its own through DSMEM and publishes it; after a second cluster
+// barrier every CTA scales and updates its own rows.  The panel's other columns are swapped in global memory as before.
+__device__ __forceinline__ void argmax_combine(double &best, int &bi, double ov, int oi) {
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+struct PanelCand { double val; int idx; int pad; };
+__global__ void __launch_bounds__(1024) lu_panel_cluster_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, int jb, int ib,
+                                                               int slice, int *__restrict__ ipiv, int *__restrict__ info) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) double psm[];
+    double *s = psm;                                                        // [IB][slice], column-major
+    PanelCand *s_cand = reinterpret_cast<PanelCand *>(psm + (size_t)IB * slice);   // this CTA's candidate (read by the cluster)
+    double *s_u = reinterpret_cast<double *>(s_cand + 1);                   // [IB] pivot row (rank 0's copy is the published one)
+    double *s_ul = s_u + IB;                                                // [IB] local copy
+    double *s_wv = s_ul + IB;                                               // [32] per-warp candidates
+    int *s_wi = reinterpret_cast<int *>(s_wv + 32);                         // [32]
+    int *s_piv = s_wi + 32;                                                 // [1]
+    int *s_pivs = s_piv + 1;                                                // [IB] pivots of the sub-panel (rank 0)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rb = k0 + jb, rows = K - rb;
+    const int r_lo = rank * slice, r_hi = min(rows, r_lo + slice);          // this CTA's rows, relative to rb
+    const int nth = (int)blockDim.x, nwarp = nth >> 5;
+    for (int c = 0; c < ib; c++) {
+        const double *g = A + (size_t)(rb + c) * lda + rb;
+        for (int r = r_lo + tid; r < r_hi; r += nth) cp_async8(&s[c * slice + r - r_lo], g + r);
+    }
+    if (rank == 0 && tid < IB) s_pivs[tid] = tid;
+    cp_async_wait_all();
+    __syncthreads();
+    for (int j = 0; j < ib; j++) {
+        // 1. first maximal |a| among this CTA's rows >= j of column j
+        double best = -1.0;
+        int bi = 0x7fffffff;
+        for (int r = r_lo + tid; r < r_hi; r += nth) {
+            if (r < j) continue;
+            const double v = fabs(s[j * slice + r - r_lo]);
+            if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) argmax_combine(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
+        if (lane == 0) { s_wv[wid] = best; s_wi[wid] = bi; }
+        __syncthreads();
+        if (wid == 0) {
+            best = lane < nwarp ? s_wv[lane] : -1.0;
+            bi = lane < nwarp ? s_wi[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) argmax_combine(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
+            if (lane == 0) { s_cand->val = best; s_cand->idx = bi; }
+        }
+        cluster.sync();
+        // 2. the pivot: warp 0 of every CTA reads all candidates through distributed shared memory
+        if (wid == 0) {
+            best = -1.0; bi = 0x7fffffff;
+            if (lane < C) {
+                const PanelCand *rc = cluster.map_shared_rank(s_cand, lane);
+                best = rc->val; bi = rc->idx;
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) argmax_combine(best, bi, __shfl_down_sync(0xffffffffu, best, o), __shfl_down_sync(0xffffffffu, bi, o));
+            best = __shfl_sync(0xffffffffu, best, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+            if (bi == 0x7fffffff) bi = j;                                   // a column of NaNs: no interchange (as idamax returns the first)
+            if (lane == 0) { *s_piv = bi; if (rank == 0) s_pivs[j] = bi; }
+            // 3. rank 0 owns the diagonal rows (j < ib <= slice): exchange row j with the pivot row, publish the pivot row
+            if (rank == 0) {
+                const int po = bi / slice;
+                if (lane < ib) {
+                    double *mine = s + lane * slice + j;
+                    double *theirs = cluster.map_shared_rank(s, po) + lane * slice + (bi - po * slice);
+                    const double a = *mine, b = *theirs;
+                    *theirs = a; *mine = b;
+                    s_u[lane] = b;
+                }
+                if (lane == 0) {
+                    ipiv[rb + j] = rb + bi;
+                    if (best == 0.0 && *info == 0) *info = rb + j + 1;      // exactly singular (LAPACK's info > 0)
+                }
+            }
+        }
+        cluster.sync();
+        // 4. scale column j and update columns j+1.. of this CTA's rows below the diagonal
+        if (tid < ib) s_ul[tid] = cluster.map_shared_rank(s_u, 0)[tid];
+        __syncthreads();
+        const double pv = s_ul[j], rcp = pv == 0.0 ? 0.0 : 1.0 / pv;
+        for (int r = r_lo + tid; r < r_hi; r += nth) {
+            if (r <= j) continue;
+            const int o = r - r_lo;
+            const double l = s[j * slice + o] * rcp;
+            s[j * slice + o] = l;
+            for (int c = j + 1; c < ib; c++) s[c * slice + o] -= l * s_ul[c];
+        }
+        // (the next column's arg-max reads the rows this thread has just updated: same row-to-thread map, no barrier needed)
+    }
+    for (int c = 0; c < ib; c++) {
+        double *g = A + (size_t)(rb + c) * lda + rb;
+        for (int r = r_lo + tid; r < r_hi; r += nth) g[r] = s[c * slice + r - r_lo];
+    }
+    __syncthreads();
+    // the panel's other columns (rank 0, one thread per column): the ib row interchanges, applied in order on a register
+    // copy of the <= 2·ib rows they touch (all loads in flight at once, instead of one L2 round trip per interchange);
+    // for the columns to the right, rows [jb, jb+ib) then become rows of U: u = L_bb⁻¹ a_b with L_bb from shared memory
+    if (rank == 0 && tid < nb && (tid < jb || tid >= jb + ib)) {
+        double *col = A + (size_t)(k0 + tid) * lda + rb;
+        double top[IB], low[IB];
+        int pv[IB];
+#pragma unroll
+        for (int i = 0; i < IB; i++) { pv[i] = i < ib ? s_pivs[i] : i; top[i] = i < ib ? col[i] : 0.0; }
+#pragma unroll
+        for (int i = 0; i < IB; i++) low[i] = (i < ib && pv[i] >= ib) ? col[pv[i]] : 0.0;
+        // value currently stored in relative row r: diagonal rows live in top[], pivot rows below in low[] (slot of the FIRST
+        // interchange that touches that row)
+#pragma unroll
+        for (int i = 0; i < IB; i++) {
+            if (i < ib && pv[i] != i) {
+                if (pv[i] < ib) {                                     // both rows inside the diagonal block
+                    double t = top[i];
+#pragma unroll
+                    for (int m = 0; m < IB; m++) if (m == pv[i]) { top[i] = top[m]; top[m] = t; }
+                } else {
+                    int slot = i;
+#pragma unroll
+                    for (int m = IB - 1; m >= 0; m--) if (m < i && pv[m] == pv[i]) slot = m;      // same row picked before
+                    double t = top[i];
+#pragma unroll
+                    for (int m = 0; m < IB; m++) if (m == slot) { top[i] = low[m]; low[m] = t; }
+                }
+            }
+        }
+        if (tid >= jb + ib) {                                         // right of the sub-panel: rows of U
+#pragma unroll
+            for (int i = 1; i < IB; i++) {
+                if (i < ib) {
+                    double sacc = top[i];
+#pragma unroll
+                    for (int jj = 0; jj < IB; jj++) if (jj < i) sacc -= s[jj * slice + i] * top[jj];
+                    top[i] = sacc;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < IB; i++) if (i < ib) col[i] = top[i];
+#pragma unroll
+        for (int i = 0; i < IB; i++) {
+            bool first = i < ib && pv[i] >= ib;
+#pragma unroll
+            for (int m = 0; m < IB; m++) if (m < i && pv[m] == pv[i]) first = false;
+            if (first) col[pv[i]] = low[i];
+        }
+    }
+    cluster.sync();           // nobody reads remote shared memory any more
+}
+
 // ---- the panel's columns right of a factored sub-panel: a_r -= L_rb u with u = the ib rows of U the panel kernel
 // solved in place; grid: (row tiles of 256, columns)
-constexpr int IB = 8;
 __global__ void __launch_bounds__(256) lu_panel_update_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int jb, int ib) {
     __shared__ double u[IB];
     const int c = k0 + jb + ib + blockIdx.y;            // column being updated
@@ -141,13 +314,60 @@ __global__ void lu_swap_kernel(double *__restrict__ A, int64_t lda, int K, int k
     }
 }
 
+// ---- the same interchanges as ONE permutation of the <= 2·nb rows they touch: lu_perm_kernel (one warp) composes the nb
+// swaps into (row, source row) pairs, lu_permute_kernel gathers every column's affected entries and scatters them — two
+// global round trips per column instead of 2·nb dependent ones (46 -> a few µs per panel at K = 2 561)
+struct PanelPerm { int n; int row[2 * NB]; int src[2 * NB]; };
+__global__ void __launch_bounds__(32) lu_perm_kernel(int k0, int nb, const int *__restrict__ ipiv, PanelPerm *__restrict__ out) {
+    __shared__ int row[2 * NB], cur[2 * NB];      // affected rows; cur[i] = original row whose content sits in row[i] now
+    __shared__ int n;
+    __shared__ int piv[NB];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < nb; i += 32) { row[i] = k0 + i; cur[i] = k0 + i; piv[i] = ipiv[k0 + i]; }
+    if (lane == 0) n = nb;
+    __syncwarp();
+    for (int j = 0; j < nb; j++) {
+        const int p = piv[j];
+        if (p == k0 + j) continue;                 // warp-uniform
+        int slot = -1;
+        if (p < k0 + nb) slot = p - k0;
+        else {
+            for (int i = nb + lane; i < n; i += 32) if (row[i] == p) slot = i;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) slot = max(slot, __shfl_xor_sync(0xffffffffu, slot, o));
+            if (slot < 0) {
+                slot = n;
+                if (lane == 0) { row[slot] = p; cur[slot] = p; n = slot + 1; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { const int t = cur[j]; cur[j] = cur[slot]; cur[slot] = t; }
+        __syncwarp();
+    }
+    if (lane == 0) out->n = n;
+    for (int i = lane; i < n; i += 32) { out->row[i] = row[i]; out->src[i] = cur[i]; }
+}
+__global__ void __launch_bounds__(2 * NB) lu_permute_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb, const PanelPerm *__restrict__ pp) {
+    const int n = pp->n, i = threadIdx.x;
+    const int dst = i < n ? pp->row[i] : 0, src = i < n ? pp->src[i] : 0;
+    for (int c = blockIdx.x; c < K - nb; c += gridDim.x) {
+        double *col = A + (size_t)(c >= k0 ? c + nb : c) * lda;      // skip the panel's own columns
+        double v = 0.0;
+        if (i < n && src != dst) v = col[src];
+        __syncthreads();
+        if (i < n && src != dst) col[dst] = v;
+        __syncthreads();
+    }
+}
+
 // ---- U12 = L11^{-1} A12: the nb×nb unit lower triangle in shared memory, one column of A12 per thread
-__global__ void __launch_bounds__(128) lu_trsm_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb) {
+__global__ void __launch_bounds__(64) lu_trsm_kernel(double *__restrict__ A, int64_t lda, int K, int k0, int nb) {
     __shared__ double L[NB][NB + 1];
     for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
         const int r = e % nb, c = e / nb;
-        L[r][c] = A[(size_t)(k0 + c) * lda + k0 + r];
+        cp_async8(&L[r][c], &A[(size_t)(k0 + c) * lda + k0 + r]);
     }
+    cp_async_wait_all();
     __syncthreads();
     const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= K) return;
@@ -155,12 +375,12 @@ __global__ void __launch_bounds__(128) lu_trsm_kernel(double *__restrict__ A, in
     double x[NB];
 #pragma unroll
     for (int i = 0; i < NB; i++) x[i] = i < nb ? col[i] : 0.0;
+    // column-oriented: after step j, x[j] is final and every x[i], i > j, has had its j-th term subtracted — the same
+    // subtractions in the same order per entry as the row-oriented loop, but NB-1-j independent operations per step
 #pragma unroll
-    for (int i = 1; i < NB; i++) {
-        double s = x[i];
+    for (int j = 0; j < NB - 1; j++) {
 #pragma unroll
-        for (int j = 0; j < i; j++) s -= L[i][j] * x[j];
-        x[i] = s;
+        for (int i = j + 1; i < NB; i++) x[i] -= L[i][j] * x[j];
     }
 #pragma unroll
     for (int i = 0; i < NB; i++) if (i < nb) col[i] = x[i];
@@ -178,12 +398,15 @@ __global__ void __launch_bounds__(128) lu_gemm_kernel(double *__restrict__ A, in
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int e = tid; e < 64 * NB; e += 128) {
         const int i = e & 63, k = e >> 6;
-        As[k * kPitch + i] = (k < nb && r0 + i < K) ? A[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
+        const bool ok = k < nb && r0 + i < K;
+        cp_async8(&As[k * kPitch + i], ok ? &A[(size_t)(k0 + k) * lda + r0 + i] : A, ok);
     }
     for (int e = tid; e < 64 * NB; e += 128) {
         const int k = e & 63, j = e >> 6;
-        Bs[j * kPitch + k] = (k < nb && c0 + j < K) ? A[(size_t)(c0 + j) * lda + k0 + k] : 0.0;
+        const bool ok = k < nb && c0 + j < K;
+        cp_async8(&Bs[j * kPitch + k], ok ? &A[(size_t)(c0 + j) * lda + k0 + k] : A, ok);
     }
+    cp_async_wait_all();
     __syncthreads();
     const int wr = (w & 1) * 32, wc = (w >> 1) * 32;      // this warp's 32×32 corner inside the tile
     double acc[4][4][2];
@@ -267,6 +490,9 @@ __global__ void rhs_update_kernel(const double *__restrict__ A, int64_t lda, int
     }
 }
 
+constexpr size_t kPanelSmemMax = 208 * 1024;
+inline size_t panel_cluster_smem(int slice) { return ((size_t)IB * slice + 2 + 2 * IB + 32) * sizeof(double) + 48 * sizeof(int); }
+
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -289,11 +515,36 @@ namespace skk {
 cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaStream_t stream, float *ms_gemm = nullptr) {
     constexpr size_t kGemmSmem = (size_t)2 * NB * kPitch * sizeof(double);      // 69 632 bytes
     cudaError_t e = cudaFuncSetAttribute(lu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmemMax);
+    static const int no_cluster = [] { const char *v = getenv("SK_LU_NO_CLUSTER"); return v ? atoi(v) : 0; }();
+    // scratch of the composed row permutation of a panel: stream-ordered allocation, freed when the factorisation's work is done
+    PanelPerm *perm = nullptr;
+    if (e == cudaSuccess && !no_cluster && cudaMallocAsync(reinterpret_cast<void **>(&perm), sizeof(PanelPerm), stream) != cudaSuccess) { perm = nullptr; (void)cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), stream);
     for (int k0 = 0; k0 < K && e == cudaSuccess; k0 += NB) {
         const int nb = std::min(NB, K - k0);
         for (int jb = 0; jb < nb; jb += IB) {
             const int ib = std::min(IB, nb - jb);
+            // sub-panel in the shared memory of a cluster of 1..8 CTAs (about 512 rows each); beyond 8 × 3 200 rows, or with
+            // SK_LU_NO_CLUSTER=1 (experiments), the global-memory kernel
+            const int rows = K - (k0 + jb);
+            // about 512 rows per CTA: measured faster than one CTA holding the whole sub-panel (36 vs 27 µs per sub-panel at
+            // K = 2 561) — a 160 KB dynamic allocation between kernels with small ones makes the SMs reconfigure their
+            // shared-memory carve-out at every launch
+            int C = 1;
+            while (C < 8 && rows > C * 512) C *= 2;
+            const int slice = (((rows + C - 1) / C) + 31) & ~31;
+            const size_t psmem = panel_cluster_smem(slice);
+            if (!no_cluster && psmem <= kPanelSmemMax) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(slice <= 512 ? 256 : slice <= 1024 ? 512 : 1024); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, A, lda, K, k0, nb, jb, ib, slice, ipiv, info);
+                if (e != cudaSuccess) return e;
+            } else
             lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, jb, ib, ipiv, info);
             const int right = nb - jb - ib, below = K - (k0 + jb + ib);
             if (right > 0) {
@@ -303,10 +554,17 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
             }
             count_launch();
         }
-        if (K - nb > 0) lu_swap_kernel<<<(K - nb + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb, ipiv);
+        if (K - nb > 0) {
+            if (perm) {
+                lu_perm_kernel<<<1, 32, 0, stream>>>(k0, nb, ipiv, perm);
+                lu_permute_kernel<<<std::min(K - nb, 2 * 148), 2 * NB, 0, stream>>>(A, lda, K, k0, nb, perm);
+                count_launch();
+            } else
+                lu_swap_kernel<<<(K - nb + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb, ipiv);
+        }
         const int rest = K - k0 - nb;
         if (rest > 0) {
-            lu_trsm_kernel<<<(rest + 127) / 128, 128, 0, stream>>>(A, lda, K, k0, nb);
+            lu_trsm_kernel<<<(rest + 63) / 64, 64, 0, stream>>>(A, lda, K, k0, nb);
             dim3 grid((unsigned)((rest + 63) / 64), (unsigned)((rest + 63) / 64));
             cudaEvent_t g0 = nullptr, g1 = nullptr;
             if (ms_gemm) { cudaEventCreate(&g0); cudaEventCreate(&g1); cudaEventRecord(g0, stream); }
@@ -321,6 +579,7 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
         count_launch(1);      // the swap kernel
         e = cudaGetLastError();
     }
+    if (perm) cudaFreeAsync(perm, stream);
     return e;
 }
 
@@ -414,7 +673,10 @@ extern "C" int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, d
     for (int r = 0; r < reps; r++) {
         CKS(cudaMemcpy(A_dev, copy.p, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
         CKS(cudaEventRecord(e0, nullptr));
+        const auto h0 = std::chrono::steady_clock::now();
         CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr));
+        const auto h1 = std::chrono::steady_clock::now();
+        if (getenv("SK_LU_TRACE")) fprintf(stderr, "lu_factor K=%lld: host enqueue %.3f ms\n", (long long)K, std::chrono::duration<double, std::milli>(h1 - h0).count());
         CKS(cudaEventRecord(e1, nullptr));
         CKS(cudaEventSynchronize(e1));
         float t = 0;
