@@ -99,8 +99,8 @@ typedef struct sk_plan_info {
     int64_t H;              /* parent dimension (Smolyak) or N */
     int32_t E;              /* doubles per output element for nvec == 1 */
     int32_t fast_path;      /* linear_combination fast kernel: 0 direct only, 1 nested (run program),
-                               2 nested with compile-time unrolled leaves, 3 nested for any ∂ specification
-                               (univariate: 1) */
+                               2 nested with compile-time unrolled leaves, 3 nested for any ∂ specification,
+                               4 unrolled second-order-jet leaves (∂ requests of total order <= 2) (univariate: 1) */
     int64_t n_runs;         /* level-1 runs of the traversal (K_2) */
     double flops_per_point_fast;    /* closed-form FP64 flop count of the fast kernel, per point */
     double flops_per_point_direct;  /* F_direct of SURVEY.md §8(d): what the reference executes */

@@ -493,6 +493,8 @@ __global__ void rhs_update_kernel(const double *__restrict__ A, int64_t lda, int
 constexpr size_t kPanelSmemMax = 208 * 1024;
 inline size_t panel_cluster_smem(int slice) { return ((size_t)IB * slice + 2 + 2 * IB + 32) * sizeof(double) + 48 * sizeof(int); }
 
+constexpr size_t kLuScratchBytes = sizeof(PanelPerm);
+
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -512,14 +514,14 @@ namespace skk {
 // In-place LU with partial pivoting of the column-major K×K matrix A (leading dimension lda); ipiv[i] = row swapped with
 // row i (0-based), *info = index + 1 of the first exactly-zero pivot or 0.  ms_gemm (optional): device time of the trailing
 // updates (the DMMA part).
-cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaStream_t stream, float *ms_gemm = nullptr) {
+// `scratch` (optional): kLuScratchBytes of device memory for the composed row permutation of a panel; without it the
+// interchanges are applied one by one.
+cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaStream_t stream, float *ms_gemm = nullptr, void *scratch = nullptr) {
     constexpr size_t kGemmSmem = (size_t)2 * NB * kPitch * sizeof(double);      // 69 632 bytes
     cudaError_t e = cudaFuncSetAttribute(lu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmemMax);
     static const int no_cluster = [] { const char *v = getenv("SK_LU_NO_CLUSTER"); return v ? atoi(v) : 0; }();
-    // scratch of the composed row permutation of a panel: stream-ordered allocation, freed when the factorisation's work is done
-    PanelPerm *perm = nullptr;
-    if (e == cudaSuccess && !no_cluster && cudaMallocAsync(reinterpret_cast<void **>(&perm), sizeof(PanelPerm), stream) != cudaSuccess) { perm = nullptr; (void)cudaGetLastError(); }
+    PanelPerm *perm = no_cluster ? nullptr : static_cast<PanelPerm *>(scratch);
     if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), stream);
     for (int k0 = 0; k0 < K && e == cudaSuccess; k0 += NB) {
         const int nb = std::min(NB, K - k0);
@@ -579,7 +581,6 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
         count_launch(1);      // the swap kernel
         e = cudaGetLastError();
     }
-    if (perm) cudaFreeAsync(perm, stream);
     return e;
 }
 
@@ -634,7 +635,8 @@ extern "C" int sk_collocation_solve(const sk_plan *plan, const double *y, int nr
     std::vector<double> grid((size_t)K * d);
     int rc = sk_grid(&plan->basis, plan->has_tr ? plan->tr : nullptr, grid.data());
     if (rc != SK_OK) return rc;
-    DevBuf dx, dA, dB, dwork, dpiv, dinfo;
+    DevBuf dx, dA, dB, dwork, dpiv, dinfo, dscr;
+    CKS(dscr.alloc(kLuScratchBytes));
     CKS(dx.alloc(grid.size() * sizeof(double)));
     CKS(dA.alloc((size_t)K * K * sizeof(double)));
     CKS(dB.alloc((size_t)K * nrhs * sizeof(double)));
@@ -647,7 +649,7 @@ extern "C" int sk_collocation_solve(const sk_plan *plan, const double *y, int nr
     if (rc != SK_OK) return rc;
     // right-hand sides y[K][nrhs] (the layout of Vector{SVector{nrhs}}) stay row-major on the device
     CKS(cudaMemcpyAsync(dB.p, y, (size_t)K * nrhs * sizeof(double), (flags & SK_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
-    CKS(skk::lu_factor((double *)dA.p, K, (int)K, (int *)dpiv.p, (int *)dinfo.p, stream));
+    CKS(skk::lu_factor((double *)dA.p, K, (int)K, (int *)dpiv.p, (int *)dinfo.p, stream, nullptr, dscr.p));
     int info = 0;
     CKS(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CKS(cudaStreamSynchronize(stream));
@@ -662,7 +664,8 @@ extern "C" int sk_collocation_solve(const sk_plan *plan, const double *y, int nr
 // mean device time; *tflops = (2/3)·K³ / time.  Used by profiles/run_solve.py.
 extern "C" int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, double *tflops, double *ms_gemm) {
     if (!A_dev || K < 1 || K > 46340 || reps < 1 || !ms || !tflops) SK_FAIL(SK_ERR_ARGUMENT, "bad argument");
-    DevBuf copy, piv, info;
+    DevBuf copy, piv, info, scr;
+    CKS(scr.alloc(kLuScratchBytes));
     CKS(copy.alloc((size_t)K * K * sizeof(double)));
     CKS(piv.alloc((size_t)K * sizeof(int)));
     CKS(info.alloc(sizeof(int)));
@@ -674,7 +677,7 @@ extern "C" int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, d
         CKS(cudaMemcpy(A_dev, copy.p, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
         CKS(cudaEventRecord(e0, nullptr));
         const auto h0 = std::chrono::steady_clock::now();
-        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr));
+        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr, nullptr, scr.p));
         const auto h1 = std::chrono::steady_clock::now();
         if (getenv("SK_LU_TRACE")) fprintf(stderr, "lu_factor K=%lld: host enqueue %.3f ms\n", (long long)K, std::chrono::duration<double, std::milli>(h1 - h0).count());
         CKS(cudaEventRecord(e1, nullptr));
@@ -689,7 +692,7 @@ extern "C" int sk_lu_benchmark(double *A_dev, int64_t K, int reps, double *ms, d
     if (ms_gemm) {
         float g = 0;
         CKS(cudaMemcpy(A_dev, copy.p, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToDevice));
-        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr, &g));
+        CKS(skk::lu_factor(A_dev, K, (int)K, (int *)piv.p, (int *)info.p, nullptr, &g, scr.p));
         CKS(cudaDeviceSynchronize());
         *ms_gemm = g;
     }
