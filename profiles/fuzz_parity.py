@@ -43,6 +43,7 @@ for it in range(N):
     u = np.clip((rng.random((n, d)) - 0.5) * 2.2, -0.97, 0.97) if use_tr else np.clip((rng.random((n, d)) - 0.5) * 2.5, -1, 1)
     y = orc.transform_from_batch(trs_or, u) if use_tr else u
     spec = ospec = None
+    parts = None
     nvec = 1
     if kind == "gradient":
         spec, ospec = sk.gradient(d), orc.gradient_spec(d)
@@ -65,6 +66,8 @@ for it in range(N):
     elif kind == "block":
         nvec = int(rng.choice([2, 3, 5, 8, 17, 30, 40, 70, 130]))
     theta = rng.standard_normal(K if nvec == 1 else (K, nvec))
+    if os.environ.get("SK_FUZZ_VERBOSE"):
+        print(json.dumps({"it": it, "code": code, "d": d, "B": B, "M": M, "kind": str(kind), "nvec": nvec, "tr": bool(use_tr), "n": n}), file=sys.stderr, flush=True)
     pts = spec(y) if spec is not None else y
     want = orc.smolyak_lincomb(code, d, B, M, theta, y, trs=trs_or, spec=ospec)
     scale = orc.smolyak_lincomb(code, d, B, M, theta, y, trs=trs_or, spec=ospec, absmode=True)
@@ -82,9 +85,13 @@ for it in range(N):
     if kind != "block":
         m = min(n, 24)
         bw = orc.smolyak_basis_at(code, d, B, M, y[:m], trs=trs_or, spec=ospec)                 # (K, m, E)
-        bg = np.asarray(sk.basis_at(basis, spec(y[:m]) if spec is not None else y[:m]))
-        bg = bg[:, :, None] if bg.ndim == 2 else bg
-        ok_basis = same(bg, bw.transpose(1, 0, 2))
+        try:
+            bg = np.asarray(sk.basis_at(basis, spec(y[:m]) if spec is not None else y[:m]))
+            bg = bg[:, :, None] if bg.ndim == 2 else bg
+            ok_basis = same(bg, bw.transpose(1, 0, 2))
+        except Exception as ex_:      # a refused or failed launch is a failure of the sweep, reported with its configuration
+            ok_basis = False
+            print(json.dumps({"basis_at_error": str(ex_)[-160:], "E": int(bw.shape[2]), "parts": parts if kind == "general" else None}), flush=True)
         paths[("basis_at", int(bw.shape[2]))] = paths.get(("basis_at", int(bw.shape[2])), 0) + 1
     with np.errstate(all="ignore"):
         err = float(np.nanmax(np.where(scale > 0, np.abs(fa - want) / scale, np.where(fa == want, 0.0, np.inf)))) if fa.size else 0.0

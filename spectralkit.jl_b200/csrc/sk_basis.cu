@@ -611,9 +611,11 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
     row_cap = std::min(row_cap, 1 + d * (int)plan.H);
     const int half_cap = (int)((budget / 2 - xj_bytes - stage_bytes > 0 ? budget / 2 - xj_bytes - stage_bytes : 0) / ((size_t)JW * P * 8));
     if (half_cap >= 1 + d * (int)std::min<int64_t>(plan.H, 16)) row_cap = std::min(row_cap, half_cap);
-    // one slice of kWarps·TW terms must fit in any case: every term adds at most d rows (plain values: min(d, B), the
-    // factors with index != 1)
-    row_cap = std::max(row_cap, kWarps * tw * (plan.ncomp == 0 ? std::min(d, plan.basis.B) : d) + 1);
+    // one slice of kWarps·TW terms must fit in any case: every term adds at most min(d, B) rows (its factors with index
+    // != 1; index 1 is the shared row 0 for every kind of request).  (The bound used to be d rows per term, which pushed
+    // 9- and 10-dimensional InteriorGrid bases with second-order requests past the shared memory of an SM: found by the
+    // parity sweep, profiles/r2_fuzz_parity.jsonl.)
+    row_cap = std::max(row_cap, kWarps * tw * std::min(d, std::max(plan.basis.B, 1)) + 1);
 
     ProgramCache &pc = cache();
     ProgramCache::Entry *en = nullptr;

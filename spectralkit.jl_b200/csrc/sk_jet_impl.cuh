@@ -306,9 +306,14 @@ constexpr bool jet_built_c(int gk, int LL, int R) {
 constexpr int jet_treg_c(int LL, int) { return LL <= 2 ? LL : 2; }      // 42 registers per table; 256 threads × four shared tables fit
 constexpr int jet_loopd_c(int gk, int LL, int R, int MODE) {
     const long n = gk == SK_GRID_INTERIOR ? nterms<SK_GRID_INTERIOR>(LL, R) : gk == SK_GRID_ENDPOINT ? nterms<SK_GRID_ENDPOINT>(LL, R) : nterms<SK_GRID_INTERIOR2>(LL, R);
+#ifdef SK_JET_LOOPD6
+    if (LL == 6) return SK_JET_LOOPD6;                      // experiments
+#endif
     if (LL <= 2) return 99;                                 // both tables in registers: nothing to loop over
     if (n * (MODE == 3 ? 3 : 2) <= 1200) return 99;         // small leaves: straight-line code
-    const int want = n * (MODE == 3 ? 3 : 2) <= 6000 ? LL : LL - 1;   // larger ones loop the top one or two dimensions
+    // larger ones loop the top dimension; the diagonal jet of the largest leaves also the one below it (measured at
+    // (InteriorGrid2, 6, 4), first looped dimension 4 / 5 / 6: diagonal jet 804 / 954 / 775 Mpoints/s, full jet 545 / 613 / 668)
+    const int want = (MODE == 2 && n > 2000) ? LL - 1 : LL;
     return want > jet_treg_c(LL, MODE) ? want : jet_treg_c(LL, MODE) + 1;
 }
 constexpr int jet_nt_c(int LL, int) { return LL >= 5 ? 256 : 256; }

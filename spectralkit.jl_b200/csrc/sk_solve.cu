@@ -545,7 +545,10 @@ cudaError_t lu_factor(double *A, int64_t lda, int K, int *ipiv, int *info, cudaS
                 at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
                 e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, A, lda, K, k0, nb, jb, ib, slice, ipiv, info);
-                if (e != cudaSuccess) return e;
+                if (e != cudaSuccess) {      // no cluster launch on this device / partition: the global-memory kernel does the same
+                    (void)cudaGetLastError();
+                    lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, jb, ib, ipiv, info);
+                }
             } else
             lu_panel_kernel<<<1, 1024, 0, stream>>>(A, lda, K, k0, nb, jb, ib, ipiv, info);
             const int right = nb - jb - ib, below = K - (k0 + jb + ib);

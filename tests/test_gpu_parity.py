@@ -421,6 +421,20 @@ def test_smolyak_basis_at_large_tables_bit_identical(orc):
         assert same(o[:, :50], want) and (o[:, 50:] == -7.0).all()
 
 
+def test_smolyak_basis_at_second_order_request_on_nine_dimensional_interior_grid(orc):
+    # regression (parity sweep, round 2): the chunk-size floor counted d table rows per term instead of min(d, B) and asked
+    # for more shared memory than an SM has — InteriorGrid d = 9, 10 with B = 3 and a second-order request was refused
+    rng = np.random.default_rng(910)
+    for d, parts in ((9, [(0, 0, 0, 0, 0, 0, 0, 0, 2)]), (10, [(2,), (0, 0, 0, 1)])):
+        basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid(), sk.SmolyakParameters(3), d)
+        spec = sk.partial(*parts[0])
+        for q in parts[1:]:
+            spec = spec | sk.partial(*q)
+        x = rand_pm1(rng, (40, d))
+        want = orc.smolyak_basis_at(0, d, 3, 3, x, spec=orc.deriv_spec(parts, d))      # (K, n, E)
+        assert same(sk.basis_at(basis, spec(x)), want.transpose(1, 0, 2))
+
+
 def test_smolyak_collocation_at_own_grid(orc):
     basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(3), 3)
     Cm = sk.collocation_matrix(basis)
@@ -535,6 +549,24 @@ def test_smolyak_second_order_jet_subsets_and_transformations(orc):
         got = sk.linear_combination(basis @ ct, theta, spec(y), allow_rational_d2=True)
         assert got.shape == want.shape and within(got, want, scale)
         assert same(sk.linear_combination(basis @ ct, theta, spec(y), allow_rational_d2=True, exact=True), want)
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 257, 1000])
+def test_smolyak_second_order_jet_ragged_batches(orc, n):
+    # partial CTAs (256 points each), a single point; the request's columns must be the only memory written
+    rng = np.random.default_rng(n)
+    d, B = 3, 3
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.EndpointGrid(), sk.SmolyakParameters(B), d)
+    parts = [(0, 1, 1), (2,)]
+    spec = sk.partial(*parts[0]) | sk.partial(*parts[1])
+    ospec = orc.deriv_spec(parts, d)
+    assert sk.get_plan(basis, 0, spec).info.fast_path == 4
+    theta = rng.standard_normal(sk.dimension(basis))
+    x = rand_pm1(rng, (n, d))
+    want = orc.smolyak_lincomb(1, d, B, B, theta, x, spec=ospec)
+    scale = orc.smolyak_lincomb(1, d, B, B, theta, x, spec=ospec, absmode=True)
+    got = sk.linear_combination(basis, theta, spec(x))
+    assert got.shape == want.shape and within(got, want, scale)
 
 
 def test_smolyak_general_spec_fast_transformed(orc):
