@@ -581,8 +581,12 @@ inline bool leaf_single_enabled() { static const bool on = getenv("SK_LEAF_NO_SI
 // Smolyak setting), and budget 4 at d = 7, 8
 constexpr bool leaf_single_deep_c(int gk, int LL, int R) {
     if (gk == SK_GRID_INTERIOR) return false;
-    return (R == 3 && LL >= 7 && LL <= 12 && LL != 8) || (R == 4 && (LL == 7 || LL == 8));
+    return (R == 3 && LL >= 7 && LL <= 12 && LL != 8) || (R == 4 && LL >= 7 && LL <= 10);
 }
+// budget 4 in nine and ten dimensions (9 361 / 13 441 terms for InteriorGrid2): every dimension from the fifth up runs
+// per-block loops, so the code is the leaves of dimensions 1..4 plus a few dozen small loop bodies, and four register
+// tables leave shared memory to θ (107 KB at d = 10)
+constexpr bool leaf_single_deep_looped_c(int LL, int R) { return R == 4 && (LL == 9 || LL == 10); }
 constexpr bool leaf_single_built_c(int gk, int LL, int R, bool grad) {
     if (leaf_single_deep_c(gk, LL, R)) return true;
     // InteriorGrid (ℓ = 3^b) budget 4 at five and six dimensions (2 641 / 4 361 terms) exists only here: inside a
@@ -612,6 +616,7 @@ constexpr int leaf_ell_c(int gk, int b) {
 }
 constexpr bool leaf_single_looped_c(int gk, int LL, int R) { return LL == 2 && gk != SK_GRID_ENDPOINT && leaf_ell_c(gk, R) > 27; }
 constexpr int leaf_single_treg_c(int gk, int LL, int R, bool grad) {
+    if (leaf_single_deep_looped_c(LL, R)) return 4;
     if (LL > 6) return leaf_treg_c(LL, grad);
     if (leaf_single_looped_c(gk, LL, R)) return LL - 1 < SK_SL_TREG ? LL - 1 : SK_SL_TREG;
     if (gk == SK_GRID_INTERIOR2 && LL == 6 && R == 5) return 3;      // θ (85 KB) + three shared-memory tables fit, four do not
@@ -634,6 +639,7 @@ constexpr bool leaf_single_big_c(int gk, int LL, int R) {
 // first looped dimension; the host's coefficient layout (smolyak_leaf_theta_map) follows it
 constexpr int leaf_single_loopd_c(int gk, int LL, int R, bool grad) {
     if (leaf_single_looped_c(gk, LL, R)) return leaf_single_treg_c(gk, LL, R, grad) + 1;
+    if (leaf_single_deep_looped_c(LL, R)) return 5;
     const int base = leaf_loopd_c(LL, grad);
     if (leaf_single_big_c(gk, LL, R)) {
         const int lo = leaf_single_treg_c(gk, LL, R, grad) + 1, want = grad ? SK_BIG_LOOPD_G : SK_BIG_LOOPD_V;
@@ -678,6 +684,8 @@ cudaError_t dispatch_leaf_single_deep(int LL, int R, const LeafParams &q, cudaSt
     if (R == 4) switch (LL) {
     case 7: return launch_leaf_single<GK, GRAD, 7, 4>(q, stream);
     case 8: return launch_leaf_single<GK, GRAD, 8, 4>(q, stream);
+    case 9: return launch_leaf_single<GK, GRAD, 9, 4>(q, stream);
+    case 10: return launch_leaf_single<GK, GRAD, 10, 4>(q, stream);
     }
     return cudaErrorNotSupported;
 }
