@@ -12,11 +12,11 @@ K = sk.dimension(basis)
 gen = torch.Generator(device="cuda").manual_seed(7)
 x = torch.rand((n, 6), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for nvec in (2, 3, 4, 6, 8, 12, 16, 32):
+for nvec in (2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64):
     th = torch.randn((K, nvec), generator=gen, device="cuda", dtype=torch.float64)
     for _ in range(2):
         sk.linear_combination(basis, th, x)
     torch.cuda.synchronize()
     e0.record(); out = sk.linear_combination(basis, th, x); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"path_max": os.environ.get("SK_LEAF_PER_VECTOR_MAX", "default"), "nvec": nvec, "points": n, "ms": ms, "Mpoints_per_s": n / ms / 1e3}), flush=True)
+    print(json.dumps({"path_max": os.environ.get("SK_LEAF_PER_VECTOR_MAX", "default"), "vec_max": os.environ.get("SK_VEC_MAX", "default"), "nvec": nvec, "points": n, "ms": ms, "Mpoints_per_s": n / ms / 1e3}), flush=True)

@@ -440,6 +440,16 @@ static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *t
             CK(cudaMalloc(&p->d_tree, tree.size() * sizeof(uint16_t)));
             CK(cudaMemcpy(p->d_tree, tree.data(), tree.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
+        if (p->ncomp == 0 && p->fast_kernel == 2 && skk::smolyak_vec_supported(*p)) {
+            for (int w = 0; w < 2; w++) {
+                std::vector<uint32_t> vmap;
+                p->vslots[w] = skk::smolyak_vec_theta_map(*p, w ? 4 : 2, &vmap);
+                if ((int64_t)vmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
+                CK(cudaMalloc(&p->d_vthmap[w], vmap.size() * sizeof(uint32_t)));
+                CK(cudaMemcpy(p->d_vthmap[w], vmap.data(), vmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            }
+            p->vec_ok = true;
+        }
         if (p->fast_kernel == 4) {
             std::vector<uint32_t> thmap;
             p->theta_slots = skk::smolyak_jet_theta_map(*p, &thmap);
@@ -486,6 +496,7 @@ sk_plan::~sk_plan() {
     if (d_runs) cudaFree(d_runs);
     if (d_units) cudaFree(d_units);
     if (d_thmap) cudaFree(d_thmap);
+    for (int w = 0; w < 2; w++) if (d_vthmap[w]) cudaFree(d_vthmap[w]);
     if (d_fac) cudaFree(d_fac);
     if (d_tree) cudaFree(d_tree);
     if (d_bprog) cudaFree(d_bprog);
@@ -528,11 +539,24 @@ static int leaf_per_vector_max() {
     return v;
 }
 
+// crossover of the multi-vector leaf kernels with the DMMA kernel (measured: profiles/r2_small_nvec.jsonl); SK_VEC_MAX
+// overrides (0 disables them: experiments)
+static int vec_max() {
+    static const int v = [] { const char *e = getenv("SK_VEC_MAX"); return e ? atoi(e) : 40; }();
+    return v;
+}
+
 // one device-resident evaluation on `stream`
 int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, const double *d_x, int64_t n,
                        double *d_out, bool exact, cudaStream_t stream) {
     if (plan->basis.kind == SK_BASIS_CHEBYSHEV) {
         CK(skk::uni_lincomb(plan->basis.N, plan->tr[0], plan->order, exact, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    // a few coefficient vectors on a one-leaf basis: four (then two) vectors per launch share every Chebyshev value
+    // (sk_vec_impl.cuh); the DMMA kernel takes over above vec_max() vectors
+    if (!exact && nvec >= 2 && nvec <= vec_max() && plan->vec_ok) {
+        CK(skk::smolyak_vec_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
     // a few coefficient vectors: one unrolled-leaf launch per vector beats the 8-wide DMMA tile (values only)

@@ -93,6 +93,9 @@ struct sk_plan {
     int bprog_F = 0, bprog_HL = 0;
     uint16_t *d_tree = nullptr;  // prefix tree of the component table (general nested kernel)
     std::vector<int> tree_lvl;   // first prefix of every level, then the total
+    uint32_t *d_vthmap[2] = {nullptr, nullptr};   // coefficient maps of the two- and four-vector leaf kernels (sk_vec.cu)
+    int64_t vslots[2] = {0, 0};
+    bool vec_ok = false;         // plain values on a one-leaf basis: the multi-vector leaf kernels serve K×nvec blocks
     int jet_mode = 0;            // second-order-jet leaf kernel (sk_jet.cu): 2 value/gradient/diagonal, 3 full Hessian jet
     int8_t jet_col[32]{};        // jet component -> output column (-1: not requested)
     int fast_kernel = 0;         // 0 none (direct only), 1 generic nested, 2 unrolled leaves, 3 general nested (any ∂ spec),

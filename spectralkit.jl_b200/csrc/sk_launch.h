@@ -47,6 +47,16 @@ double smolyak_leaf_flops(const sk_plan &plan);
 int smolyak_leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
                          std::vector<uint32_t> *map);
 
+// one coefficient vector of a K×nvec block (θ[k·theta_stride], out[p·out_stride]) through the one-vector leaf kernel
+cudaError_t smolyak_leaf_lincomb_strided(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
+                                         double *out, int64_t out_stride, cudaStream_t stream);
+
+// ---- Smolyak, two or four coefficient vectors per launch on unrolled leaves (sk_vec.cu): values, one-leaf bases
+bool smolyak_vec_supported(const sk_plan &plan);
+int64_t smolyak_vec_theta_map(const sk_plan &plan, int V, std::vector<uint32_t> *map);
+cudaError_t smolyak_vec_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out,
+                                cudaStream_t stream);
+
 // ---- Smolyak, second-order jets on unrolled leaves (sk_jet.cu): ∂ requests of total order <= 2 on bases that are one leaf
 bool smolyak_jet_supported(sk_plan &plan);       // also fixes plan.jet_mode / plan.jet_col
 int64_t smolyak_jet_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);

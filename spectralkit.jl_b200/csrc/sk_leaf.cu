@@ -83,6 +83,10 @@ int64_t smolyak_leaf_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) 
 
 static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
                                             double *out, int64_t out_stride, cudaStream_t stream);
+cudaError_t smolyak_leaf_lincomb_strided(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
+                                         double *out, int64_t out_stride, cudaStream_t stream) {
+    return n == 0 ? cudaSuccess : smolyak_leaf_lincomb_one(plan, theta, theta_stride, x, n, out, out_stride, stream);
+}
 
 // Decides whether the unrolled-leaf kernel serves the plan and, if so, fixes its leaf depth (plan.leaf_LL) and CTA
 // shape (plan.leaf_cta).  SK_LEAF_LL=n caps the depth (experiments).

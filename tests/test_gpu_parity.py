@@ -621,6 +621,42 @@ def test_smolyak_block_fast(orc, code, d, B, nvec, n):
     assert same(sk.linear_combination(basis, theta, x, exact=True), want)
 
 
+@pytest.mark.parametrize("code,d,B", [(0, 1, 4), (0, 3, 3), (0, 4, 4), (0, 6, 3), (1, 2, 5), (1, 4, 3), (1, 5, 4), (1, 6, 4),
+                                      (2, 1, 5), (2, 2, 5), (2, 3, 4), (2, 4, 5), (2, 5, 4), (2, 6, 4), (2, 6, 2)])
+def test_smolyak_few_coefficient_vectors(orc, code, d, B):
+    # SVector coefficients with 2..9 components on one-leaf bases: the four- and two-vector leaf kernels plus the one-vector
+    # kernel for an odd remainder (sk_vec_impl.cuh); against the oracle's generic_api.jl:114-128 with SVector θ
+    rng = np.random.default_rng(8800 + 100 * code + 10 * d + B)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    K = sk.dimension(basis)
+    for nvec, n in ((2, 300), (3, 257), (4, 1), (5, 255), (7, 64), (9, 513)):
+        theta = rng.standard_normal((K, nvec))
+        x = rand_pm1(rng, (n, d))
+        want = orc.smolyak_lincomb(code, d, B, B, theta, x)
+        scale = orc.smolyak_lincomb(code, d, B, B, theta, x, absmode=True)
+        got = sk.linear_combination(basis, theta, x)
+        assert got.shape == (n, nvec) and within(got, want, scale)
+        # every column equals the one-vector evaluation within the same tolerance (different summation grouping is not allowed
+        # to matter beyond it)
+        one = sk.linear_combination(basis, theta[:, nvec - 1].copy(), x)
+        assert within(got[:, nvec - 1], one, scale[:, nvec - 1], tau=2 * TAU)
+
+
+def test_smolyak_few_coefficient_vectors_transformed(orc):
+    rng = np.random.default_rng(8899)
+    d, B = 6, 4
+    trs = [mk_tr(orc, k, a, b) for k, a, b in MIXED6]
+    ct = sk.coordinate_transformations(*[t[0] for t in trs])
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+    y = sk.transform_from(basis, ct, rng.uniform(-0.95, 0.95, (700, d)))
+    for nvec in (2, 4, 6):
+        theta = rng.standard_normal((sk.dimension(basis), nvec))
+        want = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=[t[1] for t in trs])
+        scale = orc.smolyak_lincomb(2, d, B, B, theta, y, trs=[t[1] for t in trs], absmode=True)
+        assert within(sk.linear_combination(basis @ ct, theta, y), want, scale)
+        assert same(sk.linear_combination(basis @ ct, theta, y, exact=True), want)
+
+
 def test_smolyak_block_transformed_cfg5_shape(orc):
     # cfg 5 geometry (d = 10, B = 5, K = 77 505, 256 coefficient vectors) on a handful of points, with
     # coordinate transformations mixed in; Θ is 159 MB
