@@ -61,7 +61,7 @@ bool smolyak_jet_supported(sk_plan &plan) {
     }
     plan.jet_mode = mode;
     const int64_t slots = smolyak_jet_theta_map(plan, nullptr);
-    if (jet_smem_bytes(jet_nt_c(d, mode), d, jet_treg_c(d, mode), slots) > 200 * 1024) { plan.jet_mode = 0; return false; }
+    if (jet_smem_bytes(jet_nt_c(d, mode), d, jet_treg_c(d, mode), slots) > kJetSmemMax) { plan.jet_mode = 0; return false; }
     return true;
 }
 

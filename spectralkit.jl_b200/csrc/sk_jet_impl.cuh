@@ -297,12 +297,13 @@ cudaError_t launch_jet(const JetParams &q, cudaStream_t stream) {
 }
 
 // ---- which (family, depth, budget) are built, and their shapes (host and device agree through these)
-// budgets: up to 4 for EndpointGrid / InteriorGrid2 (2 561 terms at d = 6), up to 3 for InteriorGrid (737 terms); larger
-// bases keep the general kernel
+// budgets: up to 4 (2 561 terms at d = 6 for InteriorGrid2, 4 361 for InteriorGrid), 5 for EndpointGrid / InteriorGrid2 in
+// d <= 4; larger bases keep the general kernel (their θ does not fit next to the shared tables)
 constexpr bool jet_built_c(int gk, int LL, int R) {
     if (LL < 1 || LL > 6 || R < 1) return false;
-    return gk == SK_GRID_INTERIOR ? R <= (LL <= 4 ? 4 : 3) : R <= (LL <= 4 ? 5 : 4);
+    return gk == SK_GRID_INTERIOR ? R <= 4 : R <= (LL <= 4 ? 5 : 4);
 }
+constexpr size_t kJetSmemMax = 220 * 1024;      // the kernel has no static shared memory: 227 KB per CTA are available
 constexpr int jet_treg_c(int LL, int) { return LL <= 2 ? LL : 2; }      // 42 registers per table; 256 threads × four shared tables fit
 constexpr int jet_loopd_c(int gk, int LL, int R, int MODE) {
     const long n = gk == SK_GRID_INTERIOR ? nterms<SK_GRID_INTERIOR>(LL, R) : gk == SK_GRID_ENDPOINT ? nterms<SK_GRID_ENDPOINT>(LL, R) : nterms<SK_GRID_INTERIOR2>(LL, R);

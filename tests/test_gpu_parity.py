@@ -469,7 +469,8 @@ def test_smolyak_svector_coefficients(orc):
     (2, 3, 4, [(2, 2, 2)], 3),                               # every order up to 2 in every coordinate: 27 components
     (2, 1, 4, [(2,)], 4),
     (2, 8, 3, [(0, 0, 0, 0, 0, 0, 1, 1), (2,)], 3),          # more than six dimensions
-    (0, 6, 4, [(1, 1), (0, 0, 2)], 3),                       # 4 361 terms: no jet leaf of that size is built
+    (0, 6, 4, [(1, 1), (0, 0, 2)], 4),                       # 4 361 terms: the largest jet leaf
+    (2, 6, 5, [(1, 1), (0, 0, 2)], 3),                       # 10 625 terms: θ does not fit next to the shared tables
 ])
 def test_smolyak_general_spec_fast(orc, code, d, B, parts, path):
     rng = np.random.default_rng(4242 + d + B)
@@ -503,7 +504,7 @@ def hessian_parts(d, diag_only=False):
 
 
 @pytest.mark.parametrize("code,d,B", [
-    (0, 1, 4), (0, 2, 4), (0, 3, 3), (0, 4, 4), (0, 5, 3), (0, 6, 3),
+    (0, 1, 4), (0, 2, 4), (0, 3, 3), (0, 4, 4), (0, 5, 3), (0, 6, 3), (0, 5, 4), (0, 6, 4),
     (1, 1, 5), (1, 2, 5), (1, 3, 4), (1, 4, 2), (1, 5, 4), (1, 6, 4),
     (2, 1, 5), (2, 2, 5), (2, 3, 5), (2, 4, 4), (2, 5, 4), (2, 6, 4), (2, 6, 1), (2, 4, 5),
 ])
