@@ -580,6 +580,10 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         CK(skk::smolyak_block_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
+    if (skk::smolyak_warp_exact_serves(*plan, nvec)) {      // values / full gradient, one vector: one thread per point, shared prefix products
+        CK(skk::smolyak_tile_lincomb_exact(*plan, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
     if (!skk::smolyak_direct_fits(*plan, false)) {
         // full tables of 32 points exceed shared memory: the chunked-table kernel keeps the reference's order too
         if (!skk::smolyak_tile_lincomb_supported(*plan, nvec))

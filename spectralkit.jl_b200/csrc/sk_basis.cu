@@ -545,6 +545,126 @@ EncodeTiledFn encode_tiled() {
 }
 
 // device-resident chunk programs of a plan, one per jet width, built on first use
+// ---- bit-identical linear_combination, one coefficient vector, plain values or the full gradient [value, ∂1..∂d], d <= 8:
+// ONE THREAD PER POINT walks all terms in order (the reference's sequential sum) and forms all components of a term from
+// one set of table reads, sharing the prefix products between the components exactly as derivatives.jl:502-511 forms them
+// (((T1·T2)·…·T_{m-1})·T_m')·T_{m+1}·… — the same multiplications in the same order, so every bit agrees).  A CTA is one warp
+// with its own chunked table ([row][lane], (T, T') pairs for gradients): no CTA barrier anywhere, eight CTAs per SM.
+// The kernel above splits the components over warps (one product chain per component and warp, 7× the table reads) and the
+// direct kernel keeps full tables (two warps per SM): this one is 5–8× faster at cfg 4 (profiles/r2_exact_mode.jsonl).
+template <int D, bool GRADIENT>
+__global__ void __launch_bounds__(32) smolyak_warp_exact_kernel(const __grid_constant__ BasisParams q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    constexpr int JW = GRADIENT ? 2 : 1, NC = GRADIENT ? D + 1 : 1;
+    double2 *rows2 = reinterpret_cast<double2 *>(smem_raw) + lane;      // gradient: [row][lane] (T, T')
+    double *rows1 = reinterpret_cast<double *>(smem_raw) + lane;        // values:   [row][lane] T
+    for (int64_t p0 = (int64_t)blockIdx.x * kP; p0 < q.n; p0 += (int64_t)gridDim.x * kP) {
+        const int64_t p = min(p0 + lane, q.n - 1);
+        Jet<JW> X[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) skd::to_pm1_jet<JW>(q.tr[j], q.x[p * D + j], X[j].c);
+        __syncwarp();                                                   // the previous tile's rows are no longer read
+        if constexpr (GRADIENT) rows2[0] = make_double2(1.0, 0.0); else rows1[0] = 1.0;      // row 0: index 1, T_0 = (1, 0)
+        double s[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) s[c] = 0.0;
+        for (int ch = 0; ch < q.n_chunks; ch++) {
+            const ChunkHdr h = q.hdr[ch];
+            __syncwarp();                                               // the previous chunk's rows are no longer read
+            const uint16_t *bl = q.build + h.build_off;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const int maxidx = bl[0], cnt = bl[1];
+                if (cnt > 0) {
+                    Jet<JW> fp = skd::jet_one<JW>(), fpp = X[j], f;
+                    int nx = 0, want = bl[2];
+                    for (int i = 2; i <= maxidx; i++) {
+                        f = skd::cheb_step_exact<JW>(X[j], fp, fpp); fpp = fp; fp = f;
+                        if (i == want) {
+                            const int r = bl[3 + 2 * nx];
+                            if constexpr (GRADIENT) rows2[(size_t)r * kP] = make_double2(f.c[0], f.c[JW - 1]); else rows1[(size_t)r * kP] = f.c[0];
+                            nx++;
+                            want = nx < cnt ? bl[2 + 2 * nx] : 0;
+                        }
+                    }
+                }
+                bl += 2 + 2 * cnt;
+            }
+            __syncwarp();
+            // Terms are taken four at a time: their products are independent (only the sums are sequential, and they are added
+            // in term order), which multiplies the instruction-level parallelism of a warp that has the SM's schedulers almost to
+            // itself; the factor words and coefficients of the next four are fetched while this one is computed (warp-uniform:
+            // one broadcast each).
+            const uint4 *facp = reinterpret_cast<const uint4 *>(q.fac) + h.term0;
+            const double *thp = q.theta + h.term0;
+            auto products = [&](const uint4 &a4, double (&b)[NC]) {
+                const uint32_t fwd[4] = {a4.x, a4.y, a4.z, a4.w};
+                if constexpr (GRADIENT) {
+                    double2 v[D];
+#pragma unroll
+                    for (int j = 0; j < D; j++) v[j] = rows2[(size_t)fac_slot(fwd, j) * kP];
+                    double pre[D];
+                    pre[0] = v[0].x;
+#pragma unroll
+                    for (int j = 1; j < D; j++) pre[j] = pre[j - 1] * v[j].x;
+                    b[0] = pre[D - 1];
+#pragma unroll
+                    for (int m = 0; m < D; m++) {
+                        double bb = m == 0 ? v[0].y : pre[m > 0 ? m - 1 : 0] * v[m].y;
+#pragma unroll
+                        for (int j = m + 1; j < D; j++) bb = bb * v[j].x;
+                        b[m + 1 < NC ? m + 1 : 0] = bb;
+                    }
+                } else {
+                    double bb = rows1[(size_t)fac_slot(fwd, 0) * kP];
+#pragma unroll
+                    for (int m = 1; m < 8; m++) if (m < q.nf) bb = bb * rows1[(size_t)fac_slot(fwd, m) * kP];      // padding = row 0 = 1.0: exact
+                    b[0] = bb;
+                }
+            };
+            // generic_api.jl:114-128: multiply, then add, never fused; the first term starts the sum
+            auto accumulate = [&](int64_t k, double th, const double (&b)[NC]) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) s[c] = k == 0 ? th * b[c] : s[c] + th * b[c];
+            };
+            const uint32_t nt = h.nterms;
+            constexpr int U = 4;                                        // terms per iteration
+            uint4 fq[U];
+            double tq[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { const uint32_t tt = min((uint32_t)u, nt - 1); fq[u] = __ldg(facp + tt); tq[u] = __ldg(thp + tt); }
+            uint32_t t = 0;
+            for (; t + U <= nt; t += U) {
+                uint4 fa[U];
+                double ta[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { fa[u] = fq[u]; ta[u] = tq[u]; }
+#pragma unroll
+                for (int u = 0; u < U; u++) { const uint32_t tt = min(t + U + u, nt - 1); fq[u] = __ldg(facp + tt); tq[u] = __ldg(thp + tt); }
+                double b[U][NC];
+#pragma unroll
+                for (int u = 0; u < U; u++) products(fa[u], b[u]);
+#pragma unroll
+                for (int u = 0; u < U; u++) accumulate((int64_t)h.term0 + t + u, ta[u], b[u]);
+            }
+            // the last nt - t < U terms: their factor words are fq[0..], in order
+#pragma unroll
+            for (int u = 0; u < U - 1; u++) {
+                if (t + u < nt) {
+                    double b0[NC];
+                    products(fq[u], b0);
+                    accumulate((int64_t)h.term0 + t + u, tq[u], b0);
+                }
+            }
+        }
+        if (p0 + lane < q.n) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) q.out[(size_t)(p0 + lane) * NC + c] = s[c];
+        }
+    }
+}
+
 struct ProgramCache {
     std::mutex mu;
     struct Entry { const sk_plan *plan; int jw, device, pts; BasisProgram host; ChunkHdr *d_hdr; uint16_t *d_build, *d_fac; int tw, row_cap; };
@@ -567,6 +687,12 @@ void smolyak_tile_basis_forget(const sk_plan *plan) {
 }
 
 
+// one coefficient vector, plain values or the full gradient, d <= 8 (factor words of 8 slots): the one-thread-per-point kernel
+bool smolyak_warp_exact_serves(const sk_plan &plan, int nvec) {
+    static const int off = [] { const char *e = getenv("SK_EXACT_OLD"); return e ? atoi(e) : 0; }();
+    if (off || plan.basis.kind != SK_BASIS_SMOLYAK || nvec != 1 || plan.basis.d > 8 || plan.H > 4096) return false;
+    return plan.ncomp == 0 || plan.fast_mode == 1;
+}
 // exact-mode linear_combination for any basis size; false if the request is outside what the kernel's per-warp item
 // table holds (more than 64 components or 512 coefficient vectors)
 bool smolyak_tile_lincomb_supported(const sk_plan &plan, int nvec) {
@@ -592,7 +718,10 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
     // plain values (one double per element): two points per lane, 64 per CTA (SK_BASIS_PPL1=1: one; experiments)
     static const int ppl1 = [] { const char *e = getenv("SK_BASIS_PPL1"); return e ? atoi(e) : 0; }();
     const bool two = theta == nullptr && plan.ncomp == 0 && E == 1 && JW == 1 && !ppl1;
-    const int P = two ? 2 * kP : kP;
+    // exact linear_combination, one coefficient vector, values or the full gradient in d <= 8: one warp per CTA, one thread
+    // per point (smolyak_warp_exact_kernel); its tables are small chunks (eight CTAs per SM) under their own cache tag
+    const bool warp_exact = smolyak_warp_exact_serves(plan, nvec) && theta != nullptr;
+    const int P = two ? 2 * kP : warp_exact ? 1 : kP;                // (P doubles as the tag of the chunk-program cache)
     int tw = two ? 4 : 8;                                           // TW terms per warp tile: a power of two, 2-4 KB per tile
     while (tw > 1 && tw * E > 16) tw >>= 1;
     // TMA box: pb points × E components per row (<= 256 elements), TW rows; the sub-boxes of a staging tile start on
@@ -616,6 +745,11 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
     // 9- and 10-dimensional InteriorGrid bases with second-order requests past the shared memory of an SM: found by the
     // parity sweep, profiles/r2_fuzz_parity.jsonl.)
     row_cap = std::max(row_cap, kWarps * tw * std::min(d, std::max(plan.basis.B, 1)) + 1);
+    if (warp_exact) {
+        tw = 1;
+        row_cap = std::max(JW == 2 ? 56 : 112, kWarps * std::min(d, std::max(plan.basis.B, 1)) + 1);      // 28 KB per CTA
+        row_cap = std::min(row_cap, 1 + d * (int)plan.H);
+    }
 
     ProgramCache &pc = cache();
     ProgramCache::Entry *en = nullptr;
@@ -650,6 +784,29 @@ cudaError_t smolyak_tile_basis_at_impl(const sk_plan &plan, const double *theta,
     for (int c = 0; c < plan.ncomp; c++) for (int j = 0; j < d; j++) q.orders[c][j] = (int8_t)plan.orders[c][j];
     q.pb = pb; q.substride = substride;
     q.theta = theta; q.nvec = nvec;
+    if (theta && warp_exact) {
+        const size_t smem_w = (size_t)q.max_rows * kP * (JW == 2 ? 16 : 8);
+        const int64_t tiles_w = (n + kP - 1) / kP;
+        cudaError_t ew = cudaSuccess;
+#define SK_LAUNCH_WE(DD, G)                                                                                               \
+    do {                                                                                                                  \
+        ew = cudaFuncSetAttribute(smolyak_warp_exact_kernel<DD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w); \
+        int per_sm = 1;                                                                                                   \
+        if (ew == cudaSuccess) ew = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smolyak_warp_exact_kernel<DD, G>, kP, smem_w); \
+        const int grid = (int)std::min<int64_t>(tiles_w, (int64_t)sm_count() * std::max(per_sm, 1));                      \
+        if (ew == cudaSuccess) smolyak_warp_exact_kernel<DD, G><<<grid, kP, smem_w, stream>>>(q);                         \
+    } while (0)
+#define SK_LAUNCH_WED(DD) do { if (JW == 2) SK_LAUNCH_WE(DD, true); else SK_LAUNCH_WE(DD, false); } while (0)
+        switch (d) {
+        case 1: SK_LAUNCH_WED(1); break; case 2: SK_LAUNCH_WED(2); break; case 3: SK_LAUNCH_WED(3); break; case 4: SK_LAUNCH_WED(4); break;
+        case 5: SK_LAUNCH_WED(5); break; case 6: SK_LAUNCH_WED(6); break; case 7: SK_LAUNCH_WED(7); break; case 8: SK_LAUNCH_WED(8); break;
+        }
+#undef SK_LAUNCH_WED
+#undef SK_LAUNCH_WE
+        if (ew != cudaSuccess) return ew;
+        count_launch();
+        return cudaGetLastError();
+    }
     if (theta) {
         const size_t rows_b = ((size_t)q.max_rows * JW * kP * 8 + 127) & ~(size_t)127;
         const size_t smem_l = xj_bytes + rows_b;

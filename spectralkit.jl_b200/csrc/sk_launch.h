@@ -25,6 +25,7 @@ cudaError_t smolyak_tile_basis_at(const sk_plan &plan, const double *x, int64_t 
 void smolyak_tile_basis_forget(const sk_plan *plan);
 // bit-identical linear_combination (reference order) on the same chunked tables: any basis size
 bool smolyak_tile_lincomb_supported(const sk_plan &plan, int nvec);
+bool smolyak_warp_exact_serves(const sk_plan &plan, int nvec);      // values / full gradient, one vector, d <= 8: one thread per point
 cudaError_t smolyak_tile_lincomb_exact(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, cudaStream_t stream);
 
 // ---- Smolyak, nested run-structured evaluation (values, or value + full gradient)
