@@ -235,6 +235,12 @@ int sk_broadcast_coefficients(sk_comm *comm, double *const *theta_dev, int64_t c
 /* linear_combination over device-resident slices: device g holds points [g·per, min(n, (g+1)·per)), per = ceil(n/G),
  * in x_dev[g], and the coefficients in theta_dev[g]; plans[g] lives on the communicator's device g.
  * gather == 0: out_dev[g] = that slice's results [slice][E] (outputs stay sharded: the default of SURVEY.md §8(e)).
+ * gather == 2 (C2 fused with the compute): the same full buffers, filled without NCCL and without a pass after the compute.
+ *   Plans served by the six-dimensional leaf kernel (cfg 4) run ONE kernel per device whose threads store every result into
+ *   all devices' buffers themselves, peer to peer over NVLink (staged per warp so that remote writes are whole sectors);
+ *   other plans are evaluated in chunks whose results the copy engines push to the peers while the next chunk is
+ *   evaluated.  ms_gather then is what remains after the last kernel.  Needs peer access between all devices of the
+ *   communicator; otherwise it behaves like gather == 1.
  * gather != 0 (C2): every out_dev[g] is a full buffer of per·G rows; device g writes its slice at row g·per and an
  *   in-place ncclAllGather over NVLink completes all G copies (rows >= n are padding).
  * ms_compute / ms_gather: optional [G] arrays, device-timed duration of the two phases per device.  Synchronises. */

@@ -68,6 +68,21 @@ if need < free * 0.9:
         for h in (0, G - 1):
             ok &= bool(torch.equal(outs_f[h][lo:lo + m].cpu(), outs_s[g][:m].cpu()))
     res["gathered_equals_sharded"] = ok
+    # gather mode 2: slices pushed peer to peer over NVLink while the next chunk is computed
+    for o in outs_f: o.zero_()
+    for g in devices: torch.cuda.synchronize(g)
+    for rep in range(2):
+        msc2, msg2 = comm.linear_combination(plans, thetas, xs, n_total, outs_f, nvec=nvec, gather=2)
+    res.update({"overlapped_compute_ms_max": max(msc2), "overlapped_tail_ms_max": max(msg2),
+                "overlapped_total_ms_max": max(a + b for a, b in zip(msc2, msg2)), "nccl_total_ms_max": max(a + b for a, b in zip(msc, msg))})
+    ok2 = True
+    for g in devices:
+        lo, hi = sk.shard_bounds(n_total, G, g)
+        m = min(hi - lo, 1000)
+        for h in range(G):
+            ok2 &= bool(torch.equal(outs_f[h][lo:lo + m].cpu(), outs_s[g][:m].cpu()))
+            ok2 &= bool(torch.equal(outs_f[h][hi - m:hi].cpu(), outs_s[g][hi - lo - m:].cpu()))
+    res["overlapped_equals_sharded"] = ok2
 else:
     res["gather_skipped"] = f"full output of {need / 1e9:.1f} GB does not fit next to the shards"
 print(json.dumps(res), flush=True)

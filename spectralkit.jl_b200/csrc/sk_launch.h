@@ -44,6 +44,11 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int n
                                  double *out, cudaStream_t stream);
 double smolyak_leaf_flops(const sk_plan &plan);
 
+// fused gather: peer buffers for the calling thread's next leaf launch (sk_leaf.cu; used by sk_multi.cu)
+void smolyak_leaf_set_peers(int n, double *const *ptrs);
+bool smolyak_leaf_peers_used();
+bool smolyak_leaf_serves_peers(const sk_plan &plan);
+
 // shared-memory slot of every coefficient of Leaf<T, R> under the layout of leaf_end (sk_leaf_impl.cuh); returns the next slot
 int smolyak_leaf_map_rec(const skh::SmolyakSet &S, const std::vector<int> &blk_of, int LOOPD, int T, int R, int off, int64_t base,
                          std::vector<uint32_t> *map);

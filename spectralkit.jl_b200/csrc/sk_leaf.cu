@@ -231,10 +231,29 @@ cudaError_t smolyak_leaf_lincomb(const sk_plan &plan, const double *theta, int n
     return smolyak_leaf_lincomb_one(plan, theta, 1, x, n, out, plan.E, stream);
 }
 
+// ---- fused gather (sk_multi.cu, gather mode 2): the calling thread names up to 7 peer buffers; the next one-vector launch of
+// a plan the PEER instantiation serves stores its results there too and reports it
+namespace { thread_local int t_n_peer = 0; thread_local double *t_peer[7] = {}; thread_local bool t_peer_used = false; }
+void smolyak_leaf_set_peers(int n, double *const *ptrs) {
+    t_n_peer = n < 0 ? 0 : n > 7 ? 0 : n;
+    for (int g = 0; g < t_n_peer; g++) t_peer[g] = ptrs[g];
+    t_peer_used = false;
+}
+bool smolyak_leaf_peers_used() { return t_peer_used; }
+// the multi-budget six-dimensional kernel with the full-size CTA (cfg 4: the headline) has a PEER instantiation
+bool smolyak_leaf_serves_peers(const sk_plan &plan) {
+    return plan.fast_kernel == 2 && plan.basis.d == 6 && plan.leaf_LL == 6 && plan.leaf_cta == 1 && !leaf_single_kernel(plan);
+}
+
 static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n,
                                             double *out, int64_t out_stride, cudaStream_t stream) {
     const int d = plan.basis.d, LL = leaf_depth(plan), nup = d - LL;
     LeafParams q{};
+    if (t_n_peer > 0 && smolyak_leaf_serves_peers(plan)) {
+        q.n_peer = t_n_peer;
+        for (int g = 0; g < t_n_peer; g++) q.peer[g] = t_peer[g];
+        t_peer_used = true;
+    }
     q.x = x; q.out = out; q.theta = theta; q.units = plan.d_units; q.thmap = plan.d_thmap;
     q.theta_stride = theta_stride; q.out_stride = out_stride; q.small_cta = plan.leaf_cta >= 2 ? plan.leaf_cta : 0;
     q.n = n; q.K = plan.K; q.Kslots = plan.theta_slots; q.n_units = plan.n_units; q.D = d; q.nup = nup; q.budget = plan.basis.B;

@@ -294,6 +294,10 @@ struct LeafParams {
     int64_t theta_stride, out_stride;   // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     int D, nup;
     int budget;                   // B of the plan: no unit has a larger r
+    // fused gather (PEER instantiations, sk_multi.cu gather mode 2): the results are also stored into the full-output buffers
+    // of up to 7 other devices, peer to peer over NVLink, by the threads that computed them
+    int n_peer;
+    double *peer[7];              // already offset to this launch's first point
     sk_transform tr[SK_MAX_DIM];
 };
 
@@ -321,7 +325,7 @@ struct LeafSmem {
 // RONLY >= 0: single-budget kernel for bases that are one leaf of budget RONLY (d == LL).  The multi-budget kernel
 // holds the code of every budget <= RMAX and is register-allocated for the largest: at (LL, R) = (3, 3) it ran with
 // 254 registers and 268 spill stores per point (profiles/r1_leaf_variants.md, "single-budget kernels").
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1, bool PEER = false>
 __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_constant__ LeafParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -458,13 +462,45 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_leaf_kernel(const __grid_con
                 for (int m = 0; m < NCL; m++) __stcs(o + m, a[m]);
             }
         }
+        if constexpr (PEER) {
+            // Peer stores must be whole 32-byte sectors: a remote write is forwarded as it is issued (no merging in the local
+            // L2), and the per-thread layout [point][NCL] makes every 8-byte store a partial sector (measured: 154 GB/s per
+            // GPU at 8 GPUs).  A full warp therefore stages its 32·NCL results in the shared-memory slots of its own threads'
+            // dimension-(TREG+1) table — free until the next tile rebuilds it — and writes them out as consecutive 16-byte
+            // chunks.
+            const int lane = tid & 31;
+            const bool full = __all_sync(0xffffffffu, live);
+            const int64_t pw = p - lane;                                   // first point of this warp
+            bool vec = NCL > 1 && LL > TREG && full && ((NCL * 32) % 2 == 0);
+            if (vec) for (int g = 0; g < q.n_peer; g++) vec = vec && ((reinterpret_cast<uintptr_t>(q.peer[g] + pw * q.out_stride) & 15) == 0);
+            vec = __all_sync(0xffffffffu, vec);
+            if (vec) {
+                double *seg = reinterpret_cast<double *>(stab - lane);      // entry e of the warp: seg + e·NT·2, 64 doubles each
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < NCL; m++) { const int i = lane * NCL + m; seg[(size_t)(i >> 6) * NT * 2 + (i & 63)] = a[m]; }
+                __syncwarp();
+                for (int c = lane; c < NCL * 16; c += 32) {
+                    const int i = 2 * c;
+                    const double2 v = *reinterpret_cast<const double2 *>(seg + (size_t)(i >> 6) * NT * 2 + (i & 63));
+                    for (int g = 0; g < q.n_peer; g++) __stcs(reinterpret_cast<double2 *>(q.peer[g] + pw * q.out_stride + i), v);
+                }
+                __syncwarp();
+            } else if (live) {
+                for (int g = 0; g < q.n_peer; g++) {
+                    double *og = q.peer[g] + p * q.out_stride;
+#pragma unroll
+                    for (int m = 0; m < NCL; m++) __stcs(og + m, a[m]);
+                }
+            }
+        }
     }
 #undef UP
 }
 
-template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1>
+template <int GK, int LL, int RMAX, bool GRAD, int TREG, int MINB, int FENCE, int LOOPD, int NT, int RONLY = -1, bool PEER = false>
 cudaError_t launch_leaf(const LeafParams &q, cudaStream_t stream) {
-    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT, RONLY>;
+    auto kern = smolyak_leaf_kernel<GK, LL, RMAX, GRAD, TREG, MINB, FENCE, LOOPD, NT, RONLY, PEER>;
     const LeafSmem lay(NT, LL, TREG, q.D, q.nup, q.n_units, q.Kslots, GRAD);
     const size_t smem = lay.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -560,7 +596,11 @@ cudaError_t dispatch_leaf(int LL, const LeafParams &q, cudaStream_t stream) {
     case 3: return launch_leaf<GK, 3, leaf_rmax_c(GK, 3), GRAD, leaf_treg_c(3, GRAD), leaf_minb_c(3, GRAD), leaf_sync_c(3), leaf_loopd_c(3, GRAD), leaf_nt_c(3, GRAD)>(q, stream);
     case 4: return launch_leaf<GK, 4, leaf_rmax_c(GK, 4), GRAD, leaf_treg_c(4, GRAD), leaf_minb_c(4, GRAD), leaf_sync_c(4), leaf_loopd_c(4, GRAD), leaf_nt_c(4, GRAD)>(q, stream);
     case 5: return launch_leaf<GK, 5, leaf_rmax_c(GK, 5), GRAD, leaf_treg_c(5, GRAD), leaf_minb_c(5, GRAD), leaf_sync_c(5), leaf_loopd_c(5, GRAD), leaf_nt_c(5, GRAD)>(q, stream);
-    case 6: return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
+    case 6:
+        // six-dimensional bases (the headline): an instantiation that also stores into the other devices' buffers
+        if (q.n_peer > 0 && q.nup == 0)
+            return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD), -1, true>(q, stream);
+        return launch_leaf<GK, 6, leaf_rmax_c(GK, 6), GRAD, leaf_treg_c(6, GRAD), leaf_minb_c(6, GRAD), leaf_sync_c(6), leaf_loopd_c(6, GRAD), leaf_nt_c(6, GRAD)>(q, stream);
     case 8: return launch_leaf_budget<GK, 8, GRAD, leaf_treg_c(8, GRAD), leaf_minb_c(8, GRAD), leaf_loopd_c(8, GRAD), leaf_nt_c(8, GRAD)>(q, stream);
     case 10: return launch_leaf<GK, 10, leaf_rmax_c(GK, 10), GRAD, leaf_treg_c(10, GRAD), leaf_minb_c(10, GRAD), leaf_sync_c(10), leaf_loopd_c(10, GRAD), leaf_nt_c(10, GRAD)>(q, stream);
     case 12: return launch_leaf<GK, 12, leaf_rmax_c(GK, 12), GRAD, leaf_treg_c(12, GRAD), leaf_minb_c(12, GRAD), leaf_sync_c(12), leaf_loopd_c(12, GRAD), leaf_nt_c(12, GRAD)>(q, stream);

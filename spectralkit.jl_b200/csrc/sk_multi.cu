@@ -81,6 +81,10 @@ struct sk_comm {
     std::vector<ncclComm_t> comms;
     std::vector<cudaStream_t> streams;      // one non-blocking stream per device: kernels and collectives of a call
     std::vector<cudaEvent_t> ev0, ev1;
+    // gather mode 2 (result slices pushed to the peers over NVLink while the next chunk is computed): every pair of devices
+    // has peer access, and device g has one copy stream per destination h
+    bool peer_ok = false;
+    std::vector<std::vector<cudaStream_t>> cstreams;      // [g][h]
 };
 
 extern "C" {
@@ -124,6 +128,27 @@ int sk_comm_create(int ngpu, const int *devices, sk_comm **out) {
             return SK_ERR_CUDA;
         }
     }
+    // peer access between every pair (NVLink / NVSwitch): needed by the overlapped gather; without it mode 2 falls back to NCCL
+    c->peer_ok = ngpu > 1;
+    for (int g = 0; g < ngpu && c->peer_ok; g++)
+        for (int h = 0; h < ngpu && c->peer_ok; h++) {
+            if (h == g) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[g], devices[h]) != cudaSuccess || !can) c->peer_ok = false;
+        }
+    if (c->peer_ok) {
+        c->cstreams.assign((size_t)ngpu, std::vector<cudaStream_t>((size_t)ngpu, nullptr));
+        for (int g = 0; g < ngpu && c->peer_ok; g++) {
+            cudaSetDevice(devices[g]);
+            for (int h = 0; h < ngpu && c->peer_ok; h++) {
+                if (h == g) continue;
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[h], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->cstreams[(size_t)g][(size_t)h], cudaStreamNonBlocking);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); c->peer_ok = false; }
+            }
+        }
+    }
     cudaSetDevice(prev);
     *out = c;
     return SK_OK;
@@ -136,6 +161,8 @@ int sk_comm_destroy(sk_comm *c) {
     for (int g = 0; g < c->ngpu; g++) {
         cudaSetDevice(c->devices[(size_t)g]);
         if ((size_t)g < c->streams.size() && c->streams[(size_t)g]) { cudaStreamSynchronize(c->streams[(size_t)g]); cudaStreamDestroy(c->streams[(size_t)g]); }
+        if ((size_t)g < c->cstreams.size())
+            for (cudaStream_t s : c->cstreams[(size_t)g]) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
         if ((size_t)g < c->ev0.size() && c->ev0[(size_t)g]) cudaEventDestroy(c->ev0[(size_t)g]);
         if ((size_t)g < c->ev1.size() && c->ev1[(size_t)g]) cudaEventDestroy(c->ev1[(size_t)g]);
         if (c->comms[(size_t)g] && nccl().CommDestroy) nccl().CommDestroy(c->comms[(size_t)g]);
@@ -200,6 +227,89 @@ int sk_linear_combination_sharded_device(sk_comm *c, sk_plan *const *plans, cons
     std::vector<int> rcs((size_t)G, SK_OK);
     std::vector<std::string> msgs((size_t)G);
     std::vector<std::thread> workers;
+    if (gather == 2 && G > 1 && c->peer_ok) {
+        // C2 overlapped with the compute: every device cuts its slice into chunks; as soon as the kernel of a chunk has
+        // finished, the copy engines push that chunk's results into the full buffers of the other devices (one stream per
+        // destination, peer-to-peer over NVLink / NVSwitch) while the SMs evaluate the next chunk.  No NCCL, no second pass
+        // over the result; what remains after the last kernel is the transfer of one chunk.
+        const int64_t target = 1 << 20;                                   // points per chunk: ≈ 0.7 ms of the headline kernel
+        const int C = (int)std::max<int64_t>(1, std::min<int64_t>(16, per / target));
+        std::vector<std::vector<cudaEvent_t>> evc((size_t)G, std::vector<cudaEvent_t>((size_t)C, nullptr));
+        std::vector<std::vector<cudaEvent_t>> evd((size_t)G, std::vector<cudaEvent_t>((size_t)G, nullptr));
+        for (int g = 0; g < G; g++) {
+            workers.emplace_back([&, g]() {
+                const int64_t lo = std::min<int64_t>(n, per * g), hi = std::min<int64_t>(n, lo + per);
+                const int64_t cs = (hi - lo + C - 1) / std::max(C, 1);
+                cudaSetDevice(c->devices[(size_t)g]);
+                cudaStream_t sg = c->streams[(size_t)g];
+                cudaEventRecord(c->ev0[(size_t)g], sg);
+                // FUSED: where the plan's kernel has a peer-storing instantiation (the six-dimensional leaf kernel: cfg 4),
+                // the threads that compute a point's results store them into every device's buffer themselves — one launch,
+                // no copy at all; NVLink carries the stores while the FP64 pipe works on the next points
+                bool fused = false;
+                if (hi > lo && nvec == 1 && !(flags & SK_MODE_EXACT) && G <= 8 && skk::smolyak_leaf_serves_peers(*plans[g])) {
+                    double *peers[7];
+                    int np = 0;
+                    for (int h = 0; h < G; h++) if (h != g) peers[np++] = out_dev[h] + (size_t)lo * Eout;
+                    skk::smolyak_leaf_set_peers(np, peers);
+                    rcs[(size_t)g] = sk_linear_combination(plans[g], theta_dev[g], theta_len, nvec, x_dev[g], hi - lo, out_dev[g] + (size_t)lo * Eout,
+                                                           (flags & ~SK_MEM_HOST) | SK_MEM_DEVICE, sg);
+                    fused = skk::smolyak_leaf_peers_used();
+                    skk::smolyak_leaf_set_peers(0, nullptr);
+                    if (rcs[(size_t)g] != SK_OK) msgs[(size_t)g] = sk_last_error();
+                }
+                for (int j = 0; j < C && rcs[(size_t)g] == SK_OK && !fused; j++) {
+                    const int64_t clo = std::min<int64_t>(hi, lo + cs * j), chi = std::min<int64_t>(hi, clo + cs);
+                    if (chi <= clo) break;
+                    double *dst = out_dev[g] + (size_t)clo * Eout;
+                    rcs[(size_t)g] = sk_linear_combination(plans[g], theta_dev[g], theta_len, nvec, x_dev[g] + (size_t)(clo - lo) * i0.d, chi - clo, dst,
+                                                           (flags & ~SK_MEM_HOST) | SK_MEM_DEVICE, sg);
+                    if (rcs[(size_t)g] != SK_OK) { msgs[(size_t)g] = sk_last_error(); break; }
+                    cudaEventCreateWithFlags(&evc[(size_t)g][(size_t)j], cudaEventDisableTiming);
+                    cudaEventRecord(evc[(size_t)g][(size_t)j], sg);
+                    for (int h = 0; h < G; h++) {
+                        if (h == g) continue;
+                        cudaStream_t sc = c->cstreams[(size_t)g][(size_t)h];
+                        cudaStreamWaitEvent(sc, evc[(size_t)g][(size_t)j], 0);
+                        cudaMemcpyPeerAsync(out_dev[h] + (size_t)clo * Eout, c->devices[(size_t)h], dst, c->devices[(size_t)g],
+                                            (size_t)(chi - clo) * Eout * sizeof(double), sc);
+                    }
+                }
+                cudaEventRecord(c->ev1[(size_t)g], sg);                   // end of this device's kernels
+                for (int h = 0; h < G; h++) {                             // the call's stream finishes after its copies
+                    if (h == g) continue;
+                    cudaEventCreateWithFlags(&evd[(size_t)g][(size_t)h], cudaEventDisableTiming);
+                    cudaEventRecord(evd[(size_t)g][(size_t)h], c->cstreams[(size_t)g][(size_t)h]);
+                    cudaStreamWaitEvent(sg, evd[(size_t)g][(size_t)h], 0);
+                }
+            });
+        }
+        for (auto &w : workers) w.join();
+        int prev2 = 0;
+        cudaGetDevice(&prev2);
+        std::vector<cudaEvent_t> tail((size_t)G, nullptr);
+        for (int g = 0; g < G; g++) { cudaSetDevice(c->devices[(size_t)g]); cudaEventCreate(&tail[(size_t)g]); cudaEventRecord(tail[(size_t)g], c->streams[(size_t)g]); }
+        cudaError_t e2 = cudaSuccess;
+        for (int g = 0; g < G; g++) {
+            cudaSetDevice(c->devices[(size_t)g]);
+            cudaError_t eg = cudaStreamSynchronize(c->streams[(size_t)g]);
+            if (eg != cudaSuccess && e2 == cudaSuccess) e2 = eg;
+        }
+        for (int g = 0; g < G; g++) {
+            cudaSetDevice(c->devices[(size_t)g]);
+            if (e2 == cudaSuccess && ms_compute) cudaEventElapsedTime(&ms_compute[g], c->ev0[(size_t)g], c->ev1[(size_t)g]);
+            if (ms_gather) ms_gather[g] = 0.f;
+            if (e2 == cudaSuccess && ms_gather) cudaEventElapsedTime(&ms_gather[g], c->ev1[(size_t)g], tail[(size_t)g]);      // what the copies add after the last kernel
+            cudaEventDestroy(tail[(size_t)g]);
+            for (cudaEvent_t ev : evc[(size_t)g]) if (ev) cudaEventDestroy(ev);
+            for (cudaEvent_t ev : evd[(size_t)g]) if (ev) cudaEventDestroy(ev);
+        }
+        cudaSetDevice(prev2);
+        for (int g = 0; g < G; g++) if (rcs[(size_t)g] != SK_OK) SK_FAIL(rcs[(size_t)g], "device " + std::to_string(c->devices[(size_t)g]) + ": " + msgs[(size_t)g]);
+        CKM(e2);
+        skk::count_launch(G * (G - 1) * C);
+        return SK_OK;
+    }
     // phase 1: every device evaluates its slice on its own stream (one host thread per device: launches overlap)
     for (int g = 0; g < G; g++) {
         workers.emplace_back([&, g]() {

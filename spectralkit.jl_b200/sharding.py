@@ -110,5 +110,5 @@ class Comm:
         theta_len = int(thetas[0].shape[0])
         flags = L.SK_MEM_DEVICE | (L.SK_MODE_EXACT if exact else L.SK_MODE_FAST)
         L.check(L.lib.sk_linear_combination_sharded_device(self.handle, hp, tp, theta_len, int(nvec), xp, int(n_total), op,
-                                                           1 if gather else 0, flags, msc, msg))
+                                                           2 if gather == 2 else (1 if gather else 0), flags, msc, msg))
         return list(msc), list(msg)

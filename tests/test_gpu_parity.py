@@ -881,6 +881,40 @@ def test_device_pointers_and_sharded_driver(orc):
     assert same(Bm.cpu().numpy(), np.asarray(sk.basis_at(basis, x[:64])))
 
 
+def test_sharded_gather_fused_into_the_kernel_two_gpus(orc):
+    # gather mode 2 (needs two GPUs with peer access; skipped on one): every device's full buffer must equal the sharded results,
+    # for a plan the peer-storing leaf kernel serves (d = 6 gradient) and for one that goes through the copy engines (d = 4)
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from spectralkit_b200.sharding import Comm
+    comm = Comm([0, 1])
+    try:
+        for d, B, n in ((6, 4, 100_003), (4, 3, 2_500_001)):
+            basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
+            K = sk.dimension(basis)
+            plans = [sk.get_plan(basis, 0, sk.gradient(d), g) for g in (0, 1)]
+            per = (n + 1) // 2
+            thetas, xs, sh, full = [], [], [], []
+            th0 = torch.as_tensor(np.random.default_rng(d).standard_normal(K))
+            for g in (0, 1):
+                dev = torch.device("cuda", g)
+                thetas.append(th0.to(dev))
+                lo, hi = sk.shard_bounds(n, 2, g)
+                gen = torch.Generator(device=dev).manual_seed(50 + g)
+                xs.append(torch.rand((hi - lo, d), generator=gen, device=dev, dtype=torch.float64) * 1.98 - 0.99)
+                sh.append(torch.empty((hi - lo, d + 1), dtype=torch.float64, device=dev))
+                full.append(torch.zeros((per * 2, d + 1), dtype=torch.float64, device=dev))
+            comm.linear_combination(plans, thetas, xs, n, sh, gather=False)
+            comm.linear_combination(plans, thetas, xs, n, full, gather=2)
+            for g in (0, 1):
+                lo, hi = sk.shard_bounds(n, 2, g)
+                for h in (0, 1):
+                    assert torch.equal(full[h][lo:hi].cpu(), sh[g].cpu())
+    finally:
+        comm.close()
+
+
 def test_large_host_batch_goes_through_the_chunk_pipeline(orc):
     # > 2^22 points: the host path double-buffers chunks; results must not depend on chunking
     rng = np.random.default_rng(77)
