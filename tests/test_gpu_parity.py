@@ -890,7 +890,7 @@ def test_sharded_gather_fused_into_the_kernel_two_gpus(orc):
     from spectralkit_b200.sharding import Comm
     comm = Comm([0, 1])
     try:
-        for d, B, n in ((6, 4, 100_003), (4, 3, 2_500_001)):
+        for d, B, n in ((6, 4, 100_004), (6, 4, 100_001), (4, 3, 2_500_001)):      # aligned slices, odd slice length (scalar peer stores), copy engines
             basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(B), d)
             K = sk.dimension(basis)
             plans = [sk.get_plan(basis, 0, sk.gradient(d), g) for g in (0, 1)]
