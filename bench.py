@@ -300,6 +300,37 @@ def run_ours(args):
         gather = {"collective": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place)", "ms": float(tg.item()), "output_bytes_total": total_bytes,
                   "received_bytes_per_gpu": recv_bytes, "recv_gbs_per_gpu": recv_bytes / (float(tg.item()) * 1e-3) / 1e9,
                   "nvlink_measured_gbs_per_direction": 770.0, "own_slice_intact": ok}
+        # the same full output with the gather FUSED into the kernel: every rank's buffer is a torch symmetric-memory allocation
+        # (mapped into all ranks), and the kernel's threads store their results into all of them over NVLink
+        # (sk_linear_combination_peers).  Timed as compute + gather together.
+        try:
+            import torch.distributed._symmetric_memory as symm
+            fsym = symm.empty((per * world, D + 1), dtype=torch.float64, device=dev)
+            hdl = symm.rendezvous(fsym, dist.group.WORLD)
+            off = rank * per * (D + 1) * 8
+            peers = [int(hdl.buffer_ptrs[r]) + off for r in range(world) if r != rank]
+            mine_sym = fsym[rank * per:(rank + 1) * per]
+            with torch.cuda.stream(stream):
+                fused = False
+                for _ in range(2):
+                    fused = sk.linear_combination_peers(plan, theta, y, mine_sym, peers, stream)
+                barrier()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record(stream)
+                for _ in range(reps):
+                    sk.linear_combination_peers(plan, theta, y, mine_sym, peers, stream)
+                f1.record(stream)
+            barrier()
+            tf = torch.tensor([f0.elapsed_time(f1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            same = torch.tensor([1.0 if torch.equal(fsym, full) else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            gather["fused"] = {"what": "compute + gather in one kernel per GPU: results stored into every rank's buffer by the computing threads, peer to peer over NVLink (sk_linear_combination_peers, torch symmetric memory)",
+                               "kernel_stored_to_peers": bool(fused), "ms_compute_plus_gather": float(tf.item()),
+                               "ms_compute_then_nccl_gather": ms_per_step + float(tg.item()), "equals_nccl_result_on_every_rank": bool(same.item() == 1.0)}
+            del fsym
+        except Exception as ex:      # symmetric memory unavailable on this build / topology: the NCCL figure above stands alone
+            gather["fused"] = {"unavailable": str(ex)[:200]}
         del full
 
     if rank == 0:

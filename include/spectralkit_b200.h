@@ -249,6 +249,15 @@ int sk_linear_combination_sharded_device(sk_comm *comm, sk_plan *const *plans, c
                                          double *const *out_dev, int gather, uint32_t flags, float *ms_compute,
                                          float *ms_gather);
 
+/* The fused gather for callers that hold ONE PROCESS PER GPU (torchrun, MPI): linear_combination over this rank's
+ * device-resident slice whose results are ALSO stored into n_peer (<= 7) buffers of other GPUs — device pointers mapped into
+ * this process (CUDA IPC, torch symmetric memory, cuMem*), already offset to this slice's first row.  One coefficient vector,
+ * fast mode.  *fused = 1: the plan's kernel stored to the peers itself (plans served by the six-dimensional leaf kernel: cfg 4);
+ * *fused = 0: only `out` was written and the caller copies.  The writes are complete when the work on `stream` is.  No
+ * reference counterpart (the reference is single-threaded); north_star's "results gathered … over NVLink". */
+int sk_linear_combination_peers(const sk_plan *plan, const double *theta, int64_t theta_len, const double *x, int64_t n,
+                                double *out, double *const *peer_out, int n_peer, uint32_t flags, void *stream, int *fused);
+
 /* ---------------------------------------------------------------- measurement helpers */
 /* Measures the FP64 pipe on `device`: which = 0 DFMA (CUDA-core), 1 DMMA (mma.sync m8n8k4 f64),
  * 2 both at once (half the warps each: shows whether they share one pipe), 3 DFMA with three distinct register

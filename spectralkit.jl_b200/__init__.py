@@ -14,6 +14,6 @@ from .api import d, get_plan, fp64_peak, launch_count, smolyak_indices, grid_shu
 from . import _lib  # noqa: F401
 from . import experimental  # noqa: F401
 from .experimental import bridge, make_policy_functions, sum_of_squared_residuals, sum_abs2  # noqa: F401
-from .sharding import shard_bounds, broadcast_coefficients, gather_outputs, Comm  # noqa: F401
+from .sharding import shard_bounds, broadcast_coefficients, gather_outputs, linear_combination_peers, Comm  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -67,7 +67,7 @@ EXPORTS = ["sk_version", "sk_last_error", "sk_device_count", "sk_transform_make"
            "sk_grid", "sk_partials_canonical", "sk_plan_create", "sk_plan_destroy", "sk_plan_get_info",
            "sk_linear_combination", "sk_basis_at", "sk_transform_to", "sk_transform_from",
            "sk_linear_combination_sharded", "sk_comm_create", "sk_comm_destroy", "sk_comm_size", "sk_broadcast_coefficients",
-           "sk_linear_combination_sharded_device", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_policy_functions", "sk_sum_abs2", "sk_policy_residual_ssq",
+           "sk_linear_combination_sharded_device", "sk_linear_combination_peers", "sk_collocation_solve", "sk_is_subset_basis", "sk_augment_coefficients", "sk_coefficient_block_flops", "sk_policy_functions", "sk_sum_abs2", "sk_policy_residual_ssq",
            "sk_fp64_peak", "sk_lu_benchmark", "sk_launch_count"]
 
 if not os.path.exists(LIB_PATH):
@@ -102,6 +102,7 @@ lib.sk_comm_size.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.sk_broadcast_coefficients.argtypes = [_vp, C.POINTER(_vp), C.c_int64, C.c_int]
 lib.sk_linear_combination_sharded_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.c_int64, C.c_int, C.POINTER(_vp), C.c_int64,
                                                      C.POINTER(_vp), C.c_int, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.sk_linear_combination_peers.argtypes = [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.POINTER(_vp), C.c_int, C.c_uint32, _vp, C.POINTER(C.c_int)]
 lib.sk_is_subset_basis.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(C.c_int)]
 lib.sk_augment_coefficients.argtypes = [C.POINTER(BasisDesc), C.POINTER(Transform), C.POINTER(BasisDesc), C.POINTER(Transform), _vp, C.c_int64, C.c_int, _vp]
 lib.sk_coefficient_block_flops.argtypes = [_vp, C.c_int]

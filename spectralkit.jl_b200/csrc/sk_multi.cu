@@ -364,4 +364,21 @@ int sk_linear_combination_sharded_device(sk_comm *c, sk_plan *const *plans, cons
     return SK_OK;
 }
 
+int sk_linear_combination_peers(const sk_plan *plan, const double *theta, int64_t theta_len, const double *x, int64_t n,
+                                double *out, double *const *peer_out, int n_peer, uint32_t flags, void *stream, int *fused) {
+    if (fused) *fused = 0;
+    if (!plan || (n_peer > 0 && !peer_out)) SK_FAIL(SK_ERR_ARGUMENT, "NULL argument");
+    if (n_peer < 0 || n_peer > 7) SK_FAIL(SK_ERR_ARGUMENT, "between 0 and 7 peer buffers");
+    if (!(flags & SK_MEM_DEVICE)) SK_FAIL(SK_ERR_ARGUMENT, "sk_linear_combination_peers takes device pointers (SK_MEM_DEVICE)");
+    for (int g = 0; g < n_peer; g++) if (!peer_out[g]) SK_FAIL(SK_ERR_ARGUMENT, "NULL peer buffer");
+    const bool can = n_peer > 0 && n > 0 && !(flags & SK_MODE_EXACT) && skk::smolyak_leaf_serves_peers(*plan);
+    if (can) skk::smolyak_leaf_set_peers(n_peer, peer_out);
+    const int rc = sk_linear_combination(plan, theta, theta_len, 1, x, n, out, flags, stream);
+    if (can) {
+        if (fused) *fused = skk::smolyak_leaf_peers_used() ? 1 : 0;
+        skk::smolyak_leaf_set_peers(0, nullptr);
+    }
+    return rc;
+}
+
 }  // extern "C"

@@ -112,3 +112,19 @@ class Comm:
         L.check(L.lib.sk_linear_combination_sharded_device(self.handle, hp, tp, theta_len, int(nvec), xp, int(n_total), op,
                                                            2 if gather == 2 else (1 if gather else 0), flags, msc, msg))
         return list(msc), list(msg)
+
+
+def linear_combination_peers(plan, theta, x, out, peer_ptrs, stream=None) -> bool:
+    """`sk_linear_combination_peers`: evaluate this rank's slice (torch tensors on this rank's device: theta (K,), x (n, d),
+    out (n, E)) and store the results into the peers' buffers as well (`peer_ptrs`: device addresses of the other ranks'
+    buffers mapped into this process, already offset to this slice's first row — e.g. torch symmetric memory
+    `rendezvous(...).buffer_ptrs`).  Returns True when the kernel stored to the peers itself (the fused gather)."""
+    from . import _lib as L
+    import torch
+    n = int(x.shape[0])
+    ptrs = (C.c_void_p * max(1, len(peer_ptrs)))(*[int(p) for p in peer_ptrs])
+    fused = C.c_int(0)
+    st = C.c_void_p(int(stream.cuda_stream)) if stream is not None else C.c_void_p(int(torch.cuda.current_stream(x.device).cuda_stream))
+    L.check(L.lib.sk_linear_combination_peers(plan.handle, C.c_void_p(int(theta.data_ptr())), int(theta.shape[0]), C.c_void_p(int(x.data_ptr())), n,
+                                              C.c_void_p(int(out.data_ptr())), ptrs, len(peer_ptrs), L.SK_MEM_DEVICE | L.SK_MODE_FAST, st, C.byref(fused)))
+    return bool(fused.value)
