@@ -106,16 +106,16 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     cores = orc.max_threads()
-    sample = 60000 * cores
+    sample = 240000 * cores
     rate, cores, dt = cpu_reference_rate(sample, seed=104, steps=args.steps, warmup=min(args.warmup, 1))
-    rate1, _, _ = cpu_reference_rate(20000, seed=104, threads=1)
+    rate1, _, _ = cpu_reference_rate(80000, seed=104, threads=1)
     line = {
         "impl": "reference", "metric": "smolyak_d6_B4_linear_combination_Mpoints_per_s", "value": rate, "unit": "Mpoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_per_step": sample, "note": "Julia is not installed: the reference's CPU path is timed as its C restatement (oracle/sk_oracle.c), OpenMP over points"},
+        "config": {"workload": WORKLOAD, "points_per_step": sample, "note": "Julia is not installed: the reference's CPU path is timed as its C restatement (oracle/sk_oracle.c: per-point index state machine, direct products in the reference's order; gradient requests with the component structure known at compile time and the components in SIMD lanes, as Julia's generated code for SVector-valued expansions; gcc -O3), OpenMP over points"},
         "cpu_baseline": {"value": rate, "unit": "Mpoints/s", "cores": cores, "kind": "port", "value_1thread": rate1,
-                         "sample": f"{sample} points of the cfg 4b workload per step, all host threads; value_1thread: 20000 points on one thread"},
+                         "sample": f"{sample} points of the cfg 4b workload per step, all host threads; value_1thread: 80000 points on one thread"},
         "e2e": {"value": rate, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,11 +383,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
             cores = orc.max_threads()
-            sample = 100000 * cores
+            sample = 400000 * cores
             rate, cores, dt = cpu_reference_rate(sample, seed=104)
-            rate1, _, dt1 = cpu_reference_rate(20000, seed=104, threads=1)
+            rate1, _, dt1 = cpu_reference_rate(80000, seed=104, threads=1)
             line["cpu_baseline"] = {"value": rate, "unit": "Mpoints/s", "cores": cores, "kind": "port", "value_1thread": rate1,
-                                    "sample": f"first-seed {sample} points of the same workload, {dt:.1f} s on all host threads (+ 20000 points on one thread, {dt1:.1f} s); C restatement of the reference (Julia not installed)"}
+                                    "sample": f"first-seed {sample} points of the same workload, {dt:.1f} s on all host threads (+ 80000 points on one thread, {dt1:.1f} s); C restatement of the reference (Julia not installed)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -659,6 +659,34 @@ static int smolyak_tables(const smolyak_cfg *c, const double *y, jet *tab /* [d]
     return ORC_OK;
 }
 
+/* Full gradient [value, ∂1..∂d] (the headline request): the same per-term arithmetic as the generic loop below — every
+ * component's product formed left to right over the dimensions (derivatives.jl:502-511), then s = s + θ·b unfused
+ * (generic_api.jl:114-128) — with the component structure known at compile time, as Julia's generated code for a concrete
+ * ∂ type has it: no order lookups, the (T, T') of the term's d indices fetched once.  Bit-identical to the generic loop (the
+ * golden fixtures were written by it); only faster, so that the timed CPU baseline is not handicapped by interpretation. */
+static inline __attribute__((always_inline)) void grad_term(const int D, const jet *tab, int64_t H, const int64_t *idx, double th, double *sv, int first) {
+    /* component q in lane q of a short vector (what an SVector-valued ∂Expansion is in the reference): per dimension one
+     * vector multiply by (T, …, T, T', T, …) with T' in lane j + 1 — every lane still multiplies left to right */
+    enum { W = ORC_MAXDIM + 1 };
+    double b[W], f[W];
+    const jet *e0 = tab + idx[0] - 1;
+    for (int q = 0; q <= D; q++) b[q] = e0->c[0];
+    b[1] = e0->c[1];
+    for (int j = 1; j < D; j++) {
+        const jet *e = tab + (size_t)j * H + idx[j] - 1;
+        for (int q = 0; q <= D; q++) f[q] = e->c[0];
+        f[j + 1] = e->c[1];
+        for (int q = 0; q <= D; q++) b[q] = b[q] * f[q];
+    }
+    if (first) for (int q = 0; q <= D; q++) sv[q] = th * b[q];
+    else for (int q = 0; q <= D; q++) sv[q] = sv[q] + th * b[q];
+}
+static int is_full_gradient(const smolyak_cfg *c, int d, int ncomp) {
+    if (ncomp != d + 1) return 0;
+    for (int q = 0; q <= d; q++) for (int j = 0; j < d; j++) if (c->orders[q][j] != (q == j + 1 ? 1 : 0)) return 0;
+    return 1;
+}
+
 int orc_smolyak_lincomb(int grid_kind, int d, int B, int M, const orc_transform *tr,
                         int ncomp, const int32_t *orders, int ext2,
                         const double *theta, int nvec, const double *y, int64_t n, double *out,
@@ -669,6 +697,7 @@ int orc_smolyak_lincomb(int grid_kind, int d, int B, int M, const orc_transform 
     if (nvec < 1 || nvec > 4096) return ORC_ERR_ARGUMENT;
     if (nvec > 1 && ncomp > 0) return ORC_ERR_UNSUPPORTED;   /* no _mul(::SVector, ::∂Expansion) method */
     int err = 0;
+    const int gradfast = !absmode && ncomp > 0 && getenv("SK_ORACLE_GENERIC") == NULL && is_full_gradient(&c, d, ncomp);
 #ifdef _OPENMP
     if (nthreads < 1) nthreads = omp_get_max_threads();
 #pragma omp parallel num_threads(nthreads)
@@ -704,6 +733,18 @@ int orc_smolyak_lincomb(int grid_kind, int d, int B, int M, const orc_transform 
                 int rc2 = smolyak_tables(&c, yp, tab);
                 if (rc2 != ORC_OK) { err = rc2; continue; }
                 int64_t k = 0;
+                if (gradfast) {
+                    do {
+                        switch (d) {      /* constant trip counts: the compiler unrolls the products */
+                        case 2: grad_term(2, tab, c.H, s.indices, theta[k], sv, k == 0); break;
+                        case 3: grad_term(3, tab, c.H, s.indices, theta[k], sv, k == 0); break;
+                        case 4: grad_term(4, tab, c.H, s.indices, theta[k], sv, k == 0); break;
+                        case 6: grad_term(6, tab, c.H, s.indices, theta[k], sv, k == 0); break;
+                        default: grad_term(d, tab, c.H, s.indices, theta[k], sv, k == 0); break;
+                        }
+                        k++;
+                    } while (inc(&s));
+                } else
                 do {
                     double th = absmode ? fabs(theta[k]) : theta[k];
                     for (int q = 0; q < ncomp; q++) {
