@@ -915,6 +915,32 @@ def test_sharded_gather_fused_into_the_kernel_two_gpus(orc):
         comm.close()
 
 
+def test_linear_combination_peers_entry_on_one_gpu(orc):
+    # sk_linear_combination_peers without peers is sk_linear_combination; argument checks of the entry
+    import ctypes as C
+    import torch
+    from spectralkit_b200.sharding import linear_combination_peers
+    L = sk._lib
+    d = 6
+    basis = sk.smolyak_basis(sk.Chebyshev, sk.InteriorGrid2(), sk.SmolyakParameters(4), d)
+    plan = sk.get_plan(basis, 0, sk.gradient(d), 0)
+    theta = torch.as_tensor(np.random.default_rng(3).standard_normal(sk.dimension(basis))).cuda()
+    x = torch.rand((1000, d), device="cuda", dtype=torch.float64) * 1.98 - 0.99
+    out = torch.empty((1000, d + 1), device="cuda", dtype=torch.float64)
+    assert linear_combination_peers(plan, theta, x, out, []) is False
+    torch.cuda.synchronize()
+    assert torch.equal(out, sk.linear_combination(basis, theta, sk.gradient(d)(x)))
+    # a buffer of this device passed as its own "peer": the kernel stores there as well
+    twin = torch.zeros_like(out)
+    assert linear_combination_peers(plan, theta, x, out, [twin.data_ptr()]) is True
+    torch.cuda.synchronize()
+    assert torch.equal(twin, out)
+    fused = C.c_int(0)
+    rc = L.lib.sk_linear_combination_peers(plan.handle, C.c_void_p(theta.data_ptr()), int(theta.shape[0]), C.c_void_p(x.data_ptr()), 1000,
+                                           C.c_void_p(out.data_ptr()), None, 8, L.SK_MEM_DEVICE, None, C.byref(fused))
+    assert rc != 0      # more than seven peers / NULL array
+
+
 def test_large_host_batch_goes_through_the_chunk_pipeline(orc):
     # > 2^22 points: the host path double-buffers chunks; results must not depend on chunking
     rng = np.random.default_rng(77)
