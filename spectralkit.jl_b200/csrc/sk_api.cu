@@ -450,6 +450,14 @@ static int sk_plan_create_impl(const sk_basis_desc *basis, const sk_transform *t
             }
             p->vec_ok = true;
         }
+        if (p->ncomp == 0 && p->fast_kernel == 2 && skk::smolyak_pts_supported(*p)) {
+            std::vector<uint32_t> pmap;
+            p->pslots = skk::smolyak_pts_theta_map(*p, &pmap);
+            if ((int64_t)pmap.size() != p->K) SK_FAIL(SK_ERR_ARGUMENT, "internal error: coefficient map does not cover the basis");
+            CK(cudaMalloc(&p->d_pthmap, pmap.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(p->d_pthmap, pmap.data(), pmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            p->pts_ok = true;
+        }
         if (p->fast_kernel == 4) {
             std::vector<uint32_t> thmap;
             p->theta_slots = skk::smolyak_jet_theta_map(*p, &thmap);
@@ -497,6 +505,7 @@ sk_plan::~sk_plan() {
     if (d_units) cudaFree(d_units);
     if (d_thmap) cudaFree(d_thmap);
     for (int w = 0; w < 2; w++) if (d_vthmap[w]) cudaFree(d_vthmap[w]);
+    if (d_pthmap) cudaFree(d_pthmap);
     if (d_fac) cudaFree(d_fac);
     if (d_tree) cudaFree(d_tree);
     if (d_bprog) cudaFree(d_bprog);
@@ -546,11 +555,23 @@ static int vec_max() {
     return v;
 }
 
+// smallest batch for the two-points-per-thread values kernel (its tiles are twice as large); SK_PTS_MIN overrides,
+// SK_PTS_MIN=-1 disables the kernel (experiments)
+static int64_t pts_min_points() {
+    static const int64_t v = [] { const char *e = getenv("SK_PTS_MIN"); const int64_t x = e ? atoll(e) : (int64_t)1 << 16; return x < 0 ? INT64_MAX : x; }();
+    return v;
+}
+
 // one device-resident evaluation on `stream`
 int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, const double *d_x, int64_t n,
                        double *d_out, bool exact, cudaStream_t stream) {
     if (plan->basis.kind == SK_BASIS_CHEBYSHEV) {
         CK(skk::uni_lincomb(plan->basis.N, plan->tr[0], plan->order, exact, d_theta, nvec, d_x, n, d_out, stream));
+        return SK_OK;
+    }
+    // plain values, one vector, large batches on a one-leaf basis: two points per thread (sk_pts_impl.cuh)
+    if (!exact && nvec == 1 && plan->pts_ok && n >= pts_min_points()) {
+        CK(skk::smolyak_pts_lincomb(*plan, d_theta, d_x, n, d_out, stream));
         return SK_OK;
     }
     // a few coefficient vectors on a one-leaf basis: four (then two) vectors per launch share every Chebyshev value

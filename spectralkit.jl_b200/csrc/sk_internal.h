@@ -95,6 +95,9 @@ struct sk_plan {
     std::vector<int> tree_lvl;   // first prefix of every level, then the total
     uint32_t *d_vthmap[2] = {nullptr, nullptr};   // coefficient maps of the two- and four-vector leaf kernels (sk_vec.cu)
     int64_t vslots[2] = {0, 0};
+    uint32_t *d_pthmap = nullptr;  // coefficient map of the two-points-per-thread values kernel (sk_pts.cu)
+    int64_t pslots = 0;
+    bool pts_ok = false;
     bool vec_ok = false;         // plain values on a one-leaf basis: the multi-vector leaf kernels serve K×nvec blocks
     int jet_mode = 0;            // second-order-jet leaf kernel (sk_jet.cu): 2 value/gradient/diagonal, 3 full Hessian jet
     int8_t jet_col[32]{};        // jet component -> output column (-1: not requested)

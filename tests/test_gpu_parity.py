@@ -643,6 +643,24 @@ def test_smolyak_few_coefficient_vectors(orc, code, d, B):
         assert within(got[:, nvec - 1], one, scale[:, nvec - 1], tau=2 * TAU)
 
 
+@pytest.mark.parametrize("code,d,B", [(2, 6, 4), (2, 5, 4), (2, 3, 4), (1, 6, 4), (1, 4, 3), (0, 6, 3), (0, 4, 4), (2, 6, 2)])
+def test_smolyak_values_two_points_per_thread(orc, code, d, B):
+    # batches of 2^16 points and more take the two-points-per-thread values kernel (sk_pts_impl.cuh): ragged sizes (last tile
+    # partial, odd), checked against the oracle on a sample of rows and against the bit-identical mode on all of them
+    rng = np.random.default_rng(9100 + 100 * code + 10 * d + B)
+    basis = sk.smolyak_basis(sk.Chebyshev, GRIDS[code], sk.SmolyakParameters(B), d)
+    theta = rng.standard_normal(sk.dimension(basis))
+    for n in (65536, 70001):
+        x = rand_pm1(rng, (n, d))
+        got = sk.linear_combination(basis, theta, x)
+        rows = np.r_[0:150, n // 2:n // 2 + 150, n - 150:n]
+        want = orc.smolyak_lincomb(code, d, B, B, theta, x[rows])[:, 0]
+        scale = orc.smolyak_lincomb(code, d, B, B, theta, x[rows], absmode=True)[:, 0]
+        assert got.shape == (n,) and within(got[rows], want, scale)
+        exact = sk.linear_combination(basis, theta, x, exact=True)
+        assert np.max(np.abs(got - exact)) <= 1e-12 * max(1.0, np.max(np.abs(exact)))
+
+
 def test_smolyak_few_coefficient_vectors_transformed(orc):
     rng = np.random.default_rng(8899)
     d, B = 6, 4
