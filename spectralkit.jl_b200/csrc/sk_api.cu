@@ -562,6 +562,11 @@ static int64_t pts_min_points() {
     return v;
 }
 
+static int pts_vec_max() {
+    static const int v = [] { const char *e = getenv("SK_PTS_VEC_MAX"); return e ? atoi(e) : 56; }();
+    return v;
+}
+
 // one device-resident evaluation on `stream`
 int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, const double *d_x, int64_t n,
                        double *d_out, bool exact, cudaStream_t stream) {
@@ -570,8 +575,10 @@ int run_lincomb_device(const sk_plan *plan, const double *d_theta, int nvec, con
         return SK_OK;
     }
     // plain values, one vector, large batches on a one-leaf basis: two points per thread (sk_pts_impl.cuh)
-    if (!exact && nvec == 1 && plan->pts_ok && n >= pts_min_points()) {
-        CK(skk::smolyak_pts_lincomb(*plan, d_theta, d_x, n, d_out, stream));
+    // (also per vector of a K×nvec block up to pts_vec_max() vectors: one such launch per vector beats the multi-vector leaf
+    // kernel and, below ≈ 56 vectors, the DMMA kernel: profiles/r2_small_nvec.jsonl)
+    if (!exact && nvec >= 1 && nvec <= pts_vec_max() && plan->pts_ok && n >= pts_min_points()) {
+        CK(skk::smolyak_pts_lincomb(*plan, d_theta, nvec, d_x, n, d_out, stream));
         return SK_OK;
     }
     // a few coefficient vectors on a one-leaf basis: four (then two) vectors per launch share every Chebyshev value

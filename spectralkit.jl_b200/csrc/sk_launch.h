@@ -66,7 +66,7 @@ cudaError_t smolyak_vec_lincomb(const sk_plan &plan, const double *theta, int nv
 // ---- Smolyak, plain values with two points per thread on unrolled leaves (sk_pts.cu): one vector, one-leaf bases
 bool smolyak_pts_supported(const sk_plan &plan);
 int64_t smolyak_pts_theta_map(const sk_plan &plan, std::vector<uint32_t> *map);
-cudaError_t smolyak_pts_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n, double *out, cudaStream_t stream);
+cudaError_t smolyak_pts_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, cudaStream_t stream);
 
 // ---- Smolyak, second-order jets on unrolled leaves (sk_jet.cu): ∂ requests of total order <= 2 on bases that are one leaf
 bool smolyak_jet_supported(sk_plan &plan);       // also fixes plan.jet_mode / plan.jet_col

@@ -9,6 +9,8 @@ namespace skk {
 cudaError_t dispatch_pts_h0(int LL, int R, const PtsParams &q, cudaStream_t stream);
 cudaError_t dispatch_pts_h1(int LL, int R, const PtsParams &q, cudaStream_t stream);
 cudaError_t dispatch_pts_h2(int LL, int R, const PtsParams &q, cudaStream_t stream);
+cudaError_t smolyak_pts_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n, double *out,
+                                    int64_t out_stride, cudaStream_t stream);
 
 bool smolyak_pts_supported(const sk_plan &plan) {
     if (plan.basis.kind != SK_BASIS_SMOLYAK || plan.ncomp != 0 || plan.basis.M != plan.basis.B) return false;
@@ -25,11 +27,24 @@ int64_t smolyak_pts_theta_map(const sk_plan &plan, std::vector<uint32_t> *map) {
     return even_up(smolyak_leaf_map_rec(S, blk_of, pts_loopd_c(S.grid_kind, S.d, S.B), S.d, S.B, 0, 0, map));
 }
 
-cudaError_t smolyak_pts_lincomb(const sk_plan &plan, const double *theta, const double *x, int64_t n, double *out, cudaStream_t stream) {
+// nvec > 1: one launch per coefficient vector of the K×nvec block (θ and the results strided by nvec)
+cudaError_t smolyak_pts_lincomb(const sk_plan &plan, const double *theta, int nvec, const double *x, int64_t n, double *out, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    if (nvec > 1) {
+        for (int v = 0; v < nvec; v++) {
+            cudaError_t e = smolyak_pts_lincomb_one(plan, theta + v, nvec, x, n, out + v, nvec, stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    return smolyak_pts_lincomb_one(plan, theta, 1, x, n, out, 1, stream);
+}
+cudaError_t smolyak_pts_lincomb_one(const sk_plan &plan, const double *theta, int64_t theta_stride, const double *x, int64_t n, double *out,
+                                    int64_t out_stride, cudaStream_t stream) {
     const int d = plan.basis.d, R = plan.basis.B;
     PtsParams q{};
     q.x = x; q.out = out; q.theta = theta; q.thmap = plan.d_pthmap; q.n = n; q.K = plan.K; q.Kslots = plan.pslots;
+    q.theta_stride = theta_stride; q.out_stride = out_stride;
     for (int j = 0; j < d; j++) {
         if (plan.has_tr) q.tr[j] = plan.tr[j];
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }

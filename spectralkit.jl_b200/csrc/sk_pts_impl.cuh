@@ -153,6 +153,7 @@ struct PtsParams {
     const double *theta;
     const uint32_t *thmap;        // slot of every coefficient (layout of leaf_end with this kernel's LOOPD)
     int64_t n, K, Kslots;
+    int64_t theta_stride, out_stride;      // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
     sk_transform tr[6];
 };
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_pts_kernel(const __grid_cons
     const int tid = threadIdx.x;
     double *s_theta = reinterpret_cast<double *>(smem_raw);
     double *stab = reinterpret_cast<double *>(smem_raw + (((size_t)q.Kslots * 8 + 15) & ~(size_t)15)) + tid;
-    for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i];
+    for (int64_t i = tid; i < q.K; i += NT) s_theta[q.thmap[i]] = q.theta[i * q.theta_stride];
     __syncthreads();
     using CX = PtsCtx<TREG, LOOPD, NT>;
     for (int64_t p0 = (int64_t)blockIdx.x * NT * kPP; p0 < q.n; p0 += (int64_t)gridDim.x * NT * kPP) {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(NT, MINB) smolyak_pts_kernel(const __grid_cons
         ThRd th{s_theta, 0.0};
         PLeaf<GK, LL, R, CX>::run(cx, th, 0, a);
 #pragma unroll
-        for (int v = 0; v < kPP; v++) if (p0 + tid + (int64_t)v * NT < q.n) __stcs(q.out + p0 + tid + (int64_t)v * NT, a[v]);
+        for (int v = 0; v < kPP; v++) if (p0 + tid + (int64_t)v * NT < q.n) __stcs(q.out + (p0 + tid + (int64_t)v * NT) * q.out_stride, a[v]);
     }
 }
 
