@@ -7,6 +7,9 @@
 
 namespace skk {
 
+#ifdef SK_GPTS_HOOK
+cudaError_t smolyak_gpts_hook(const LeafParams &q, cudaStream_t stream);      // experiments (exp/gpts_variant.cu)
+#endif
 cudaError_t dispatch_leaf_g0v(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g0g(int LL, const LeafParams &q, cudaStream_t stream);
 cudaError_t dispatch_leaf_g1v(int LL, const LeafParams &q, cudaStream_t stream);
@@ -262,6 +265,9 @@ static cudaError_t smolyak_leaf_lincomb_one(const sk_plan &plan, const double *t
         else { q.tr[j].kind = SK_TR_NONE; q.tr[j].reserved = 0; q.tr[j].p0 = 0; q.tr[j].p1 = 1; }
     }
     const bool g = plan.fast_mode == 1;
+#ifdef SK_GPTS_HOOK
+    if (g && d == 6 && plan.basis.B == 4 && plan.basis.grid_kind == SK_GRID_INTERIOR2 && nup == 0 && getenv("SK_GPTS")) return smolyak_gpts_hook(q, stream);
+#endif
     if (leaf_single_kernel(plan)) {      // the basis is one leaf of budget B: single-budget kernel when built
         const int R = plan.basis.B;
         cudaError_t e = cudaErrorNotSupported;
