@@ -15,7 +15,7 @@ cudaError_t smolyak_pts_lincomb_one(const sk_plan &plan, const double *theta, in
 bool smolyak_pts_supported(const sk_plan &plan) {
     if (plan.basis.kind != SK_BASIS_SMOLYAK || plan.ncomp != 0 || plan.basis.M != plan.basis.B) return false;
     const int d = plan.basis.d, B = plan.basis.B, gk = plan.basis.grid_kind;
-    if (d > 6 || !pts_built_c(gk, d, B)) return false;
+    if (d > 8 || !pts_built_c(gk, d, B)) return false;
     return pts_smem_bytes(pts_nt_c(d), d, pts_treg_c(d), smolyak_pts_theta_map(plan, nullptr)) <= 200 * 1024;
 }
 

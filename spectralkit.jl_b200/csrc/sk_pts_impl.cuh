@@ -154,7 +154,7 @@ struct PtsParams {
     const uint32_t *thmap;        // slot of every coefficient (layout of leaf_end with this kernel's LOOPD)
     int64_t n, K, Kslots;
     int64_t theta_stride, out_stride;      // coefficient vector v of a K×nvec block: θ[k·nvec + v] → out[p·nvec + v]
-    sk_transform tr[6];
+    sk_transform tr[8];
 };
 
 constexpr size_t pts_smem_bytes(int NT, int LL, int TREG, int64_t Kslots) {
@@ -228,15 +228,16 @@ cudaError_t launch_pts(const PtsParams &q, cudaStream_t stream) {
 
 // ---- which (family, depth, budget) are built, and their shapes
 constexpr bool pts_built_c(int gk, int LL, int R) {
-    if (LL < 3 || LL > 6 || R < 2) return false;      // small leaves are bandwidth-bound already
-    return gk == SK_GRID_INTERIOR ? R <= (LL <= 4 ? 4 : 3) : R <= 4;
+    if (LL < 3 || LL > 8 || R < 2) return false;      // small leaves are bandwidth-bound already
+    if (LL > 6) return gk != SK_GRID_INTERIOR && R <= 3;      // seven and eight dimensions: budgets 2, 3 (799 / 1 121 terms)
+    return gk == SK_GRID_INTERIOR ? R <= (LL <= 4 ? 4 : 3) : R <= (LL <= 4 ? 5 : 4);
 }
 // measured at InteriorGrid2 B = 4, 2²³ points (one point per thread: d = 6 2 700, d = 5 4 983 Mpoints/s): 256 threads with three
 // register tables 3 770 / 6 802, two tables 3 870 / 6 341, 384 threads 3 487 / 6 229 (three tables), 3 179 / 6 221 (two), 320: 2 827 / 5 134
 #ifndef SK_PTS_NT
 #define SK_PTS_NT 256
 #endif
-constexpr int pts_treg_c(int LL) { return LL >= 6 ? 2 : LL < 3 ? LL : 3; }
+constexpr int pts_treg_c(int LL) { return LL == 6 ? 2 : LL < 3 ? LL : 3; }
 constexpr int pts_loopd_c(int, int, int) { return 99; }      // values-only code is short: straight-line (as the one-point kernel)
 constexpr int pts_nt_c(int) { return SK_PTS_NT; }
 
@@ -253,12 +254,15 @@ cudaError_t dispatch_pts_r(int R, const PtsParams &q, cudaStream_t stream) {
     case 2: return launch_pts_built<GK, LL, 2>(q, stream);
     case 3: return launch_pts_built<GK, LL, 3>(q, stream);
     case 4: return launch_pts_built<GK, LL, 4>(q, stream);
+    case 5: return launch_pts_built<GK, LL, 5>(q, stream);
     }
     return cudaErrorNotSupported;
 }
 template <int GK>
 cudaError_t dispatch_pts(int LL, int R, const PtsParams &q, cudaStream_t stream) {
     switch (LL) {
+    case 7: return dispatch_pts_r<GK, 7>(R, q, stream);
+    case 8: return dispatch_pts_r<GK, 8>(R, q, stream);
     case 3: return dispatch_pts_r<GK, 3>(R, q, stream);
     case 4: return dispatch_pts_r<GK, 4>(R, q, stream);
     case 5: return dispatch_pts_r<GK, 5>(R, q, stream);

@@ -643,7 +643,8 @@ def test_smolyak_few_coefficient_vectors(orc, code, d, B):
         assert within(got[:, nvec - 1], one, scale[:, nvec - 1], tau=2 * TAU)
 
 
-@pytest.mark.parametrize("code,d,B", [(2, 6, 4), (2, 5, 4), (2, 3, 4), (1, 6, 4), (1, 4, 3), (0, 6, 3), (0, 4, 4), (2, 6, 2)])
+@pytest.mark.parametrize("code,d,B", [(2, 6, 4), (2, 5, 4), (2, 3, 4), (1, 6, 4), (1, 4, 3), (0, 6, 3), (0, 4, 4), (2, 6, 2), (2, 4, 5), (1, 3, 5),
+                                      (2, 7, 3), (1, 8, 3), (2, 8, 2)])
 def test_smolyak_values_two_points_per_thread(orc, code, d, B):
     # batches of 2^16 points and more take the two-points-per-thread values kernel (sk_pts_impl.cuh): ragged sizes (last tile
     # partial, odd), checked against the oracle on a sample of rows and against the bit-identical mode on all of them
