@@ -45,7 +45,11 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool val
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 constexpr int NB = 64;           // panel width
-constexpr int IB = 8;            // sub-panel width
+#ifndef SK_LU_IB
+#define SK_LU_IB 8
+#endif
+constexpr int IB = SK_LU_IB;     // sub-panel width; measured LU times at K = 2 561 / 4 096 / 8 192: IB = 8 14.3 / 24.8 / 82.1 ms,
+                                 // 16: 13.7 / 24.7 / 82.3, 32: 15.9 / 28.1 / 178 — the per-column latency dominates either way
 constexpr int kPitch = 68;       // shared-memory pitch of the GEMM operand tiles (≡ 4 mod 16: conflict-free fragment loads)
 
 // ---- panel factorisation: columns [k0, k0+nb) of rows [k0, K); one CTA of 1024 threads
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ A, 
     const int right = nb - jb - ib, rb = k0 + jb;
     if (tid < right) {
         double *c = A + (size_t)(rb + ib + tid) * lda + rb;
-        double x[8];
+        double x[IB];
         for (int i = 0; i < ib; i++) {
             double sacc = c[i];
             for (int jj = 0; jj < i; jj++) sacc -= A[(size_t)(rb + jj) * lda + rb + i] * x[jj];
@@ -491,7 +495,7 @@ __global__ void rhs_update_kernel(const double *__restrict__ A, int64_t lda, int
 }
 
 constexpr size_t kPanelSmemMax = 208 * 1024;
-inline size_t panel_cluster_smem(int slice) { return ((size_t)IB * slice + 2 + 2 * IB + 32) * sizeof(double) + 48 * sizeof(int); }
+inline size_t panel_cluster_smem(int slice) { return ((size_t)IB * slice + 2 + 2 * IB + 32) * sizeof(double) + (48 + IB) * sizeof(int); }
 
 constexpr size_t kLuScratchBytes = sizeof(PanelPerm);
 
