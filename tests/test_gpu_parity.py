@@ -830,12 +830,17 @@ def test_no_out_of_bounds_writes_around_caller_buffers(orc):
         x6 = rand_pm1(rng, (n, 6))
         run(b6, sk.gradient(6), rng.standard_normal(K6), x6, 7)                      # leaf kernel, gradient
         run(b6, None, rng.standard_normal(K6), x6, 1)                                # leaf kernel, values
-        run(b6, None, rng.standard_normal((K6, 5)), x6, 5)                           # leaf kernel per vector (strided θ / out)
+        run(b6, None, rng.standard_normal((K6, 5)), x6, 5)                           # multi-vector leaf kernels (4 + 1 vectors, strided θ / out)
         run(b6, None, rng.standard_normal((K6, 37)), x6, 37)                         # block kernel, 64-wide tile, odd nvec
         run(b6, None, rng.standard_normal((K6, 130)), x6, 130)                       # block kernel, 256-wide tile, partial
-        run(b6, sk.partial(1, 1) | sk.partial(0, 0, 2), rng.standard_normal(K6), x6, 6)   # general nested kernel
-        run(b6, sk.gradient(6), rng.standard_normal(K6), x6, 7, exact=True)          # direct kernel, component lanes
+        run(b6, sk.partial(1, 1) | sk.partial(0, 0, 2), rng.standard_normal(K6), x6, 6)   # second-order-jet leaves (column map)
+        run(b6, sk.gradient(6), rng.standard_normal(K6), x6, 7, exact=True)          # one-thread-per-point exact kernel
         run(b8, sk.gradient(8), rng.standard_normal(K8), rand_pm1(rng, (n, 8)), 9)   # leaf kernel with the unit interpreter
+    for n in (65537, 66049):                                                         # two-points-per-thread values kernel (tiles of 512 points)
+        x6 = rand_pm1(rng, (n, 6))
+        run(b6, None, rng.standard_normal(K6), x6, 1)
+        run(b6, None, rng.standard_normal((K6, 3)), x6, 3)                           # one launch per vector, strided θ / out
+        run(b8, None, rng.standard_normal(K8), rand_pm1(rng, (n, 8)), 1)
     for n in (1, 63, 65, 200):
         run(b6, None, None, rand_pm1(rng, (n, 6)), 1, basis_at=True)                 # basis_at, values (streaming stores)
         run(b6, sk.gradient(6), None, rand_pm1(rng, (n, 6)), 7, basis_at=True)       # basis_at, staged bulk copies
