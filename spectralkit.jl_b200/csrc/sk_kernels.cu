@@ -123,6 +123,57 @@ __global__ void __launch_bounds__(256) uni_lincomb_kernel(int N, sk_transform tr
     }
 }
 
+// Fast path for large batches, PP points per thread (the thread's points are one grid stride apart: loads and stores stay
+// coalesced): θ comes from the constant bank through the uniform datapath, and every LDCU — which holds the scheduler for
+// ≈ 2.25 cycles (profiles/micro/dfma_ldcu.cu) — now feeds the fmas of PP points instead of one.
+template <int DP1, int PP>
+__global__ void __launch_bounds__(256) uni_lincomb_pts_kernel(int N, sk_transform tr, int cs, const double *__restrict__ x, int64_t n,
+                                                              double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < n; p0 += stride * PP) {
+        double t0[PP], t1[PP], tt1[PP], t2[PP], fp[PP][DP1], fpp[PP][DP1], s[PP][DP1];
+#pragma unroll
+        for (int v = 0; v < PP; v++) {
+            double xj[DP1];
+            skd::to_pm1_jet<DP1>(tr, x[min(p0 + v * stride, n - 1)], xj);
+            t0[v] = 2.0 * xj[0];
+            t1[v] = DP1 > 1 ? 2.0 * xj[DP1 > 1 ? 1 : 0] : 0.0;
+            tt1[v] = 2.0 * t1[v];
+            t2[v] = DP1 > 2 ? 2.0 * xj[DP1 > 2 ? 2 : 0] : 0.0;
+#pragma unroll
+            for (int r = 0; r < DP1; r++) { fp[v][r] = r == 0 ? 1.0 : 0.0; fpp[v][r] = xj[r]; }
+        }
+        const double th0 = c_uni_theta[cs];
+#pragma unroll
+        for (int v = 0; v < PP; v++)
+#pragma unroll
+            for (int r = 0; r < DP1; r++) s[v][r] = r == 0 ? th0 : 0.0;
+#pragma unroll 4
+        for (int k = 1; k < N; k++) {
+            const double tk = c_uni_theta[cs + k];
+#pragma unroll
+            for (int v = 0; v < PP; v++) {
+                double f[DP1];
+                f[0] = fma(t0[v], fp[v][0], -fpp[v][0]);
+                if (DP1 > 1) f[DP1 > 1 ? 1 : 0] = fma(t0[v], fp[v][DP1 > 1 ? 1 : 0], fma(t1[v], fp[v][0], -fpp[v][DP1 > 1 ? 1 : 0]));
+                if (DP1 > 2)
+                    f[DP1 > 2 ? 2 : 0] = fma(t0[v], fp[v][DP1 > 2 ? 2 : 0],
+                                             fma(tt1[v], fp[v][DP1 > 1 ? 1 : 0], fma(t2[v], fp[v][0], -fpp[v][DP1 > 2 ? 2 : 0])));
+#pragma unroll
+                for (int r = 0; r < DP1; r++) { s[v][r] = fma(tk, f[r], s[v][r]); fpp[v][r] = fp[v][r]; fp[v][r] = f[r]; }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < PP; v++) {
+            const int64_t p = p0 + v * stride;
+            if (p < n) {
+#pragma unroll
+                for (int r = 0; r < DP1; r++) out[p * DP1 + r] = s[v][r];
+            }
+        }
+    }
+}
+
 // SVector coefficients (nvec > 1), values only: θ is [N][nvec]; VC vectors per pass
 template <bool EXACT, int VC>
 __global__ void __launch_bounds__(256) uni_lincomb_nvec_kernel(int N, sk_transform tr, const double *__restrict__ theta,
@@ -185,7 +236,17 @@ static cudaError_t launch_uni(bool exact, int N, const sk_transform &tr, const d
         if (e != cudaSuccess) return e;
         e = cudaMemcpyToSymbolAsync(c_uni_theta, theta, (size_t)N * sizeof(double), (size_t)slot * kUniConstMax * sizeof(double), cudaMemcpyDeviceToDevice, stream);
         if (e != cudaSuccess) return e;
-        uni_lincomb_kernel<(DP1 <= 3 ? DP1 : 1), false, true><<<grid, threads, 0, stream>>>(N, tr, theta, slot * kUniConstMax, x, n, out);
+        // SK_UNI_PP = points per thread of the constant-bank kernel (experiments).  Measured at 2²⁶ points, cfg 2 / cfg 3:
+        // one point 43 / 21.8 Gpoints/s, two 39.6 / 20.4, four 38.4 / 20.3 — unlike the Smolyak values kernel this one gains
+        // nothing from sharing a coefficient between points (the recurrence, not θ, is most of its work): one point stays
+        static const int pp = [] { const char *e2 = getenv("SK_UNI_PP"); return e2 ? atoi(e2) : 1; }();
+        constexpr int D1 = DP1 <= 3 ? DP1 : 1;
+        if (pp == 2 || pp == 4) {
+            const int g2 = (int)std::min<int64_t>((want + pp - 1) / pp, (int64_t)sm_count() * 16);
+            if (pp == 2) uni_lincomb_pts_kernel<D1, 2><<<g2, threads, 0, stream>>>(N, tr, slot * kUniConstMax, x, n, out);
+            else uni_lincomb_pts_kernel<D1, 4><<<g2, threads, 0, stream>>>(N, tr, slot * kUniConstMax, x, n, out);
+        } else
+        uni_lincomb_kernel<D1, false, true><<<grid, threads, 0, stream>>>(N, tr, theta, slot * kUniConstMax, x, n, out);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
